@@ -1,0 +1,55 @@
+"""End-to-end pins of the CPU oracle against the only numbers the reference publishes
+for this path: the tutorial notebook's Bmax(z=0) of galaxies 22, 23, 24 of
+example/example_input.hdf5 (reference doc/magnetizer_tutorial.ipynb:673, cell 32) and
+its "Timestep became very small" log lines for galaxies 22 and 23 (:323-326)."""
+import numpy as np
+
+# Fortran gal_id -> Bmax at the last snapshot, microgauss (B0_mkG/B0 = 1: code units)
+TUTORIAL_BMAX = {22: 0.45010823, 23: 0.42917456, 24: 0.03083575}
+
+
+def test_tutorial_bmax_pins(oracle, example_input):
+    t, inputs = example_input
+    p = oracle.default_params()  # xorshift1024* stream (GCC 7/8 libgfortran), all defaults
+    ids = np.array(sorted(TUTORIAL_BMAX), np.int32)
+    r = oracle.solve_batch(p, ids, t, inputs[:, ids - 1, :], profiles=("Br",), scalars=("Bmax",), nthreads=3,
+                           want_hist=True)
+    for k, g in enumerate(ids):
+        got = r["scalars"][0][k][-1]
+        # the notebook prints 8 digits; the residual (<= 1e-6) is the root finder's 1e-7
+        # tolerance meeting unpinned GSL/libm versions.  Galaxy 24's field is set by the
+        # random floor-sign history, so this also pins the RNG stream, its seeding and the
+        # order of all draws.
+        assert abs(got / TUTORIAL_BMAX[int(g)] - 1) < 2e-6, (g, got)
+        assert r["error"][k] == 0
+    # galaxies 22 and 23 hit p_nsteps_max at their first snapshot
+    assert r["nsteps_hist"][0].max() == 20000 and r["nsteps_hist"][1].max() == 20000
+    assert r["nsteps_hist"][2].max() < 20000
+    assert r["status"][0].tobytes() == b"M" * 40
+    assert r["status"][1].tobytes() == b"-" * 7 + b"M" * 33
+    assert r["status"][2].tobytes() == b"-" * 6 + b"M" * 34
+
+
+def test_other_generator_changes_rng_dependent_galaxy_only_weakly(oracle, example_input):
+    """With GCC>=9's xoshiro256** the saturated galaxies agree to ~1e-4 and only the
+    floor-dominated galaxy 24 differs: documents why rng_kind is a parameter."""
+    t, inputs = example_input
+    p = oracle.default_params()
+    p.rng_kind = 0
+    ids = np.array([23], np.int32)
+    r = oracle.solve_batch(p, ids, t, inputs[:, ids - 1, :], profiles=("Br",), scalars=("Bmax",), nthreads=1)
+    assert abs(r["scalars"][0][0][-1] / TUTORIAL_BMAX[23] - 1) < 2e-4
+
+
+def test_invalid_galaxy_reports_error(oracle, example_input):
+    """No snapshot with r_disk >= p_rdisk_min, or a single valid snapshot -> status 'p',
+    error=.true., nothing written (input_parameters.f90:217-223, dynamo.f90:69-73)."""
+    t, inputs = example_input
+    bad = inputs[:, :2, :].copy()
+    bad[0, 0, :] = -1.0e10  # never valid
+    bad[0, 1, :] = -1.0e10
+    bad[0, 1, 5] = 3.0      # exactly one valid snapshot -> max_it - init_it == 0
+    p = oracle.default_params()
+    r = oracle.solve_batch(p, np.array([1, 2], np.int32), t, bad, nthreads=1)
+    assert r["error"].tolist() == [1, 1]
+    assert (r["profiles"] == -99999.0).all() and (r["status"] == b"-").all()
