@@ -1,0 +1,523 @@
+// mag_solver.cu -- persistent warp-per-galaxy kernel and the C ABI (include/magnetizer_b200.h).
+//
+// Replaces, for the per-galaxy dynamo path only, the reference's MPI master/worker farm
+// (source/distributor.f90:253-384) + work routine dynamo_run (source/dynamo.f90:39): the
+// farm becomes a device-side work queue (one atomic counter) drained by persistent warps,
+// each of which runs a whole galaxy history.  No collective, no host round trip between
+// snapshots; inputs are staged into HBM once per batch and read with coalesced loads
+// (snapshot index fastest), outputs are written as contiguous 101-point rows.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mag_galaxy.cuh"
+#include "mag_rk_fast.cuh"
+
+using namespace magdev;
+
+#define WARPS_PER_CTA 4
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+      return (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? MAG_ERR_NO_DEVICE : MAG_ERR_CUDA; \
+    }                                                                                          \
+  } while (0)
+
+// ------------------------------------------------------------------ dynamo_run on a warp
+// dynamo.f90:39-300.  Returns true when the reference would return error=.true.
+__device__ static bool run_galaxy(Gal& G, RkShared* rs) {
+  const mag_params_t& P = G.a->P;
+  const bool test_run = P.p_no_magnetic_fields_test_run != 0;
+  const int lane = G.lane;
+  bool elliptical = false, ok = true;
+  if (lane == 0) rng_seed(G.rng, G.a->gal_ids[G.g], P.p_random_seed, P.rng_kind);
+  __syncwarp();
+  // initialize_floor_sign (floor_field.f90:116-123)
+  G.t_last_sign_choice = 0.0;
+  (void)random_sign(G);
+  G.refresh_sign = true;
+  G.sign_nx = -1;
+  G.status = test_run ? 't' : 'M';
+  G.flags = 0; G.point_stages = 0;
+  G.last_output = false;
+  G.t = 0; G.dt = 0; G.nsteps = 20; G.time_between_inputs = 0; G.minh = 1e10; G.maxetat = 0; G.tau_min = 0;
+  reset_outputs(G);
+  load_input_parameters(G);
+  if (set_input_params(G)) return true;
+  construct_grid(G);
+  {
+    const int ids[] = {A_F0, A_F1, A_F2, A_ALP, A_BZ, A_BEQ, A_TAU, A_LKPC, A_L, A_N, A_H, A_ETAT, A_ALPK};
+    for (int k = 0; k < (int)(sizeof(ids) / sizeof(int)); k++) {
+      double* p = G.A(ids[k]);
+      for (int i = lane; i < G.nx; i += 32) p[i] = 0.0;
+    }
+    __syncwarp();
+  }
+  bool able = construct_profiles(G);
+  int it = G.init_it;
+  if (!able) {  // finish()
+    estimate_Bzmod(G);
+    make_ts_arrays(G, it);
+    return false;
+  }
+  if (G.Mgas_disk < P.Mgas_disk_min) G.flags |= MAG_FLAG_STALE_PROFILES;
+  if (G.r_disk > P.p_rdisk_min && G.Mgas_disk > P.Mgas_disk_min) {
+    init_seed_field(G);
+    estimate_Bzmod(G);
+    impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
+  }
+  bool finish_needed = false;
+  for (it = G.init_it; it <= G.max_it; it++) {
+    if (G.r_disk < P.p_rdisk_min || G.Mgas_disk < P.Mgas_disk_min) {
+      elliptical = true;
+      for (int v = 0; v < 3; v++) { double* f = G.A(A_F0 + v); for (int i = lane; i < G.nx; i += 32) f[i] = 0.0; }
+      __syncwarp();
+    } else {
+      if (elliptical) {
+        able = construct_profiles(G);
+        init_seed_field(G);
+        estimate_Bzmod(G);
+        impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
+      }
+      if (able) elliptical = false;
+    }
+    if (it != G.init_it && !elliptical) {
+      if (!adjust_grid(G)) { if (lane == 0) atomicExch(G.a->fail, MAG_ERR_NX_OVERFLOW); return true; }
+      impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
+      able = construct_profiles(G);
+      if (!able) { G.last_output = true; finish_needed = true; break; }
+    }
+    set_timestep(G, true);
+    {  // f_snapshot_beginning = f
+      for (int v = 0; v < 3; v++) {
+        const double* f = G.A(A_F0 + v); double* fb = G.A(A_FB0 + v);
+        for (int i = lane; i < G.nx; i += 32) fb[i] = f[i];
+      }
+      __syncwarp();
+    }
+    for (int fail_count = 0; fail_count <= P.p_MAX_FAILS; fail_count++) {
+      ok = true;
+      if (test_run || elliptical) {
+        double *alp = G.A(A_ALP), *bz = G.A(A_BZ);
+        for (int i = lane; i < G.nx; i += 32) { alp[i] = 0.0; bz[i] = 0.0; }
+        __syncwarp();
+        break;
+      }
+      ok = run_timesteps(G, rs);
+      if (ok) break;
+      G.status = 'm';
+      G.flags |= MAG_FLAG_RETRY;
+      set_timestep(G, false);
+      for (int v = 0; v < 3; v++) {
+        double* f = G.A(A_F0 + v); const double* fb = G.A(A_FB0 + v);
+        for (int i = lane; i < G.nx; i += 32) f[i] = fb[i];
+      }
+      __syncwarp();
+    }
+    if (!ok) {
+      G.status = 'i';
+      G.last_output = true;
+      init_seed_field(G);
+    }
+    impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
+    estimate_Bzmod(G);
+    make_ts_arrays(G, it);
+    if (G.last_output) break;
+    G.status = test_run ? 't' : 'M';
+    if (set_input_params(G)) break;
+  }
+  if (finish_needed) {  // finish() is the only writer of this snapshot
+    estimate_Bzmod(G);
+    make_ts_arrays(G, it);
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_dynamo_run(KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * WARPS_PER_CTA + wib;
+  RkShared* rs = reinterpret_cast<RkShared*>(smem_raw) + wib;
+  Gal G;
+  G.a = &a;
+  G.W = a.ws + (size_t)gw * A_COUNT * a.nxcap;
+  G.rng = &rs->rng;
+  G.lane = lane;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(a.counter, 1);
+    q = __shfl_sync(FULL, q, 0);
+    if (q >= a.ngal) break;
+    G.g = a.order ? a.order[q] : q;
+    const bool err = run_galaxy(G, rs);
+    if (lane == 0) {
+      if (a.out.error) a.out.error[G.g] = err ? 1 : 0;
+      if (a.out.nsteps) a.out.nsteps[G.g] = G.nsteps;
+      if (a.out.point_stages) a.out.point_stages[G.g] = G.point_stages;
+      if (a.out.flags) a.out.flags[G.g] = G.flags;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ cost-ordered queue
+// Longest histories first (number of valid snapshots), so that the persistent warps do not
+// end on a 40-snapshot galaxy: a counting sort on the device.
+__global__ void k_cost_hist(const double* inputs, int ngal, int nz, double rdisk_min, int* key, int* hist) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngal) return;
+  int init_it = -1, max_it = nz;
+  for (int i = 1; i <= nz; i++) {
+    double rd = inputs[(size_t)g * nz + i - 1];
+    if (rd >= rdisk_min && init_it < 0) init_it = i;
+    if (rd < 0 && init_it > 0) { max_it = i - 1; break; }
+  }
+  int k = init_it < 0 ? 0 : max_it - init_it + 1;
+  key[g] = k;
+  atomicAdd(&hist[k], 1);
+}
+__global__ void k_cost_scan(int* hist, int nz) {  // descending exclusive scan, in place
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int k = nz; k >= 0; k--) { int c = hist[k]; hist[k] = acc; acc += c; }
+  }
+}
+__global__ void k_cost_scatter(const int* key, int ngal, int* hist, int* order) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngal) return;
+  order[atomicAdd(&hist[key[g]], 1)] = g;
+}
+
+// FP64 peak micro-benchmark: independent DFMA chains, 2 flops each
+__global__ void k_dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------ host side
+struct mag_ctx {
+  mag_params_t P;
+  int device = 0;
+  int sm_count = 0;
+  int ctas_per_sm = 0;
+  int nwarps = 0;
+  int nxcap = 0;
+  double* ws = nullptr;
+  int* d_counter = nullptr;  // [0] queue head, [1] fail flag
+  int* d_hist = nullptr;
+  int* d_key = nullptr;
+  int* d_order = nullptr;
+  int order_cap = 0;
+  // staging for the host-buffer API
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double last_ms[4] = {0, 0, 0, 0};
+  int last_launches = 0;
+  int use_fast = 1;
+};
+
+extern "C" {
+
+const char* mag_last_error(void) { return g_last_error.c_str(); }
+
+void mag_params_default(mag_params_t* p) {
+  // source/global_input_parameters.f90 defaults; literals without d0 are single precision
+  // in the reference and are widened from float here
+  memset(p, 0, sizeof(*p));
+  p->abi_version = MAG_ABI_VERSION;
+  p->nsteps_0 = 1000; p->p_nsteps_max = 20000; p->p_MAX_FAILS = 6; p->p_random_seed = 17;
+  p->p_no_magnetic_fields_test_run = 0;
+  p->p_courant_v = (double)0.09f; p->p_courant_eta = (double)0.09f;
+  p->p_nx_ref = 101; p->p_nx_MAX = 10000; p->p_rmax_over_rdisk = 2.75;
+  p->frac_seed = 0.01; p->C_alp = 1.0; p->C_floor = 1.0; p->p_floor_kappa = 10.0; p->fmag = 0.5; p->R_kappa = 1.0;
+  p->p_ISM_sound_speed_km_s = 10.0; p->p_ISM_kappa = 1.0; p->p_ISM_xi = 0.25; p->p_ISM_gamma = 5.0 / 3.0;
+  p->p_ISM_turbulent_length = (double)0.1f;
+  p->p_stellarHeightToRadiusScale = 1.0 / (double)7.3f;
+  p->p_molecularHeightToRadiusScale = (double)0.032f;
+  p->p_gasScaleRadiusToStellarScaleRadius_ratio = 1.0;
+  p->p_Rmol_alpha = 0.92; p->p_Rmol_P0 = 4.787e-12;
+  p->p_rreg_to_rdisk = (double)0.1f;
+  p->p_minimum_density = 1e-30; p->p_rdisk_min = 0.5; p->Mgas_disk_min = 1e4;
+  p->rmin_over_rmax = (double)0.001f;
+  p->p_ignore_satellite_DM_haloes = 0; p->p_use_Pdm = 1; p->p_use_Pbulge = 1;
+  p->rng_kind = MAG_RNG_XORSHIFT1024S;
+  p->p_variable_timesteps = 1; p->p_simplified_pressure = 1; p->p_halo_contraction = 1; p->p_enable_P2 = 0;
+  p->Dyn_quench = 1; p->Alg_quench = 0; p->Damp = 0; p->lFloor = 1;
+  p->p_space_varying_floor = 1; p->p_time_varying_floor = 1; p->p_limit_turbulent_scale = 1;
+  p->p_allow_positive_shears = 0; p->seed_choice = 0; p->outflow_type = 0;
+}
+
+static bool params_supported(const mag_params_t& p) {
+  return p.abi_version == MAG_ABI_VERSION && p.p_variable_timesteps == 1 && p.p_simplified_pressure == 1 &&
+         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && p.Alg_quench == 0 && p.Damp == 0 &&
+         p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
+         p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice == 0 &&
+         p.outflow_type == 0 && p.p_nx_ref >= 8 && (p.rng_kind == 0 || p.rng_kind == 1) &&
+         p.p_nx_MAX >= p.p_nx_ref + 6;
+}
+
+int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
+  if (!params || !ctx_out) { set_error("null argument"); return MAG_ERR_BAD_ARGUMENT; }
+  *ctx_out = nullptr;
+  if (!params_supported(*params)) { set_error("parameter combination outside the implemented path"); return MAG_ERR_UNSUPPORTED; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { set_error("no CUDA device (this library has no CPU fallback)"); return MAG_ERR_NO_DEVICE; }
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= ndev) { set_error("device index out of range"); return MAG_ERR_BAD_ARGUMENT; }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { set_error("kernels are built for sm_100a only"); return MAG_ERR_NO_DEVICE; }
+  mag_ctx* c = new mag_ctx();
+  c->P = *params;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  const char* env_fast = getenv("MAG_DISABLE_FAST_PATH");
+  c->use_fast = (env_fast && env_fast[0] == '1') ? 0 : 1;
+  const size_t smem = sizeof(RkShared) * WARPS_PER_CTA;
+  CUDA_TRY(cudaFuncSetAttribute(k_dynamo_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dynamo_run, WARPS_PER_CTA * 32, smem));
+  if (occ < 1) { set_error("kernel does not fit on an SM"); delete c; return MAG_ERR_CUDA; }
+  c->ctas_per_sm = occ;
+  c->nwarps = c->sm_count * occ * WARPS_PER_CTA;
+  const char* env_cap = getenv("MAG_NXCAP");
+  int cap = env_cap ? atoi(env_cap) : 2048;
+  if (cap > params->p_nx_MAX) cap = params->p_nx_MAX;
+  if (cap < params->p_nx_ref + 6) cap = params->p_nx_ref + 6;
+  c->nxcap = (cap + 15) & ~15;
+  CUDA_TRY(cudaMalloc(&c->ws, (size_t)c->nwarps * A_COUNT * c->nxcap * sizeof(double)));
+  CUDA_TRY(cudaMemset(c->ws, 0, (size_t)c->nwarps * A_COUNT * c->nxcap * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&c->d_counter, 2 * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_hist, 4096 * sizeof(int)));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+  *ctx_out = c;
+  return MAG_OK;
+}
+
+void mag_destroy(mag_ctx_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->ws); cudaFree(c->d_counter); cudaFree(c->d_hist); cudaFree(c->d_key); cudaFree(c->d_order);
+  cudaFree(c->d_stage);
+  for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static int check_quantities(int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q, const int32_t* scalar_q) {
+  if (n_profile_q < 0 || n_profile_q > MAG_NPROFILE || n_scalar_q < 0 || n_scalar_q > MAG_NSCALAR) return MAG_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < n_profile_q; i++) if (profile_q[i] < 0 || profile_q[i] >= MAG_NPROFILE) return MAG_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < n_scalar_q; i++) if (scalar_q[i] < 0 || scalar_q[i] >= MAG_NSCALAR) return MAG_ERR_BAD_ARGUMENT;
+  return MAG_OK;
+}
+
+static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int32_t nz, const double* d_t,
+                        const double* d_inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
+                        const int32_t* scalar_q, const mag_outputs_t* d_out, cudaStream_t st) {
+  if (nz < 1 || nz > 4000) { set_error("nz out of range"); return MAG_ERR_BAD_ARGUMENT; }
+  if (ngal > c->order_cap) {
+    cudaFree(c->d_key); cudaFree(c->d_order);
+    c->d_key = c->d_order = nullptr; c->order_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->d_key, (size_t)ngal * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->d_order, (size_t)ngal * sizeof(int)));
+    c->order_cap = ngal;
+  }
+  int launches = 0;
+  CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, (nz + 1) * sizeof(int), st));
+  const int tb = 256, gb = (ngal + tb - 1) / tb;
+  k_cost_hist<<<gb, tb, 0, st>>>(d_inputs /* column 0 = r_disk */, ngal, nz, c->P.p_rdisk_min, c->d_key, c->d_hist);
+  k_cost_scan<<<1, 32, 0, st>>>(c->d_hist, nz);
+  k_cost_scatter<<<gb, tb, 0, st>>>(c->d_key, ngal, c->d_hist, c->d_order);
+  launches += 3;
+  KernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = c->P;
+  a.U = make_units();
+  a.ngal = ngal; a.nz = nz;
+  a.gal_ids = d_gal_ids; a.t_gyr = d_t; a.inputs = d_inputs; a.order = c->d_order;
+  a.n_profile_q = n_profile_q; a.n_scalar_q = n_scalar_q;
+  for (int i = 0; i < n_profile_q; i++) a.profile_q[i] = profile_q[i];
+  for (int i = 0; i < n_scalar_q; i++) a.scalar_q[i] = scalar_q[i];
+  a.out = *d_out;
+  a.ws = c->ws; a.nxcap = c->nxcap;
+  a.counter = c->d_counter; a.fail = c->d_counter + 1;
+  a.use_fast = c->use_fast;
+  int ctas = c->sm_count * c->ctas_per_sm;
+  const int need = (ngal + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  if (need < ctas) ctas = need;
+  const size_t smem = sizeof(RkShared) * WARPS_PER_CTA;
+  k_dynamo_run<<<ctas, WARPS_PER_CTA * 32, smem, st>>>(a);
+  launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  c->last_launches = launches;
+  return MAG_OK;
+}
+
+int mag_solve_batch_device(mag_ctx_t* c, int32_t ngal, const int32_t* d_gal_ids, int32_t nz, const double* d_t_gyr,
+                           const double* d_inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
+                           const int32_t* scalar_q, const mag_outputs_t* d_out, void* cuda_stream) {
+  if (!c || !d_out || ngal < 0) { set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT; }
+  if (check_quantities(n_profile_q, profile_q, n_scalar_q, scalar_q)) { set_error("bad quantity id"); return MAG_ERR_BAD_ARGUMENT; }
+  if (ngal == 0) return MAG_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  int rc = launch_solve(c, ngal, d_gal_ids, nz, d_t_gyr, d_inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, d_out, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  return MAG_OK;
+}
+
+int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t nz, const double* t_gyr,
+                    const double* inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
+                    const int32_t* scalar_q, const mag_outputs_t* out) {
+  if (!c || !out || ngal < 0 || !gal_ids || !t_gyr || !inputs) { set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT; }
+  if (check_quantities(n_profile_q, profile_q, n_scalar_q, scalar_q)) { set_error("bad quantity id"); return MAG_ERR_BAD_ARGUMENT; }
+  if (ngal == 0) return MAG_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t nr = c->P.p_nx_ref;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_in = al(sizeof(double) * MAG_NINPUT * ngal * nz), b_t = al(sizeof(double) * nz), b_id = al(sizeof(int32_t) * ngal);
+  const size_t b_prof = out->profiles ? al(sizeof(double) * n_profile_q * ngal * nz * nr) : 0;
+  const size_t b_scal = out->scalars ? al(sizeof(double) * n_scalar_q * ngal * nz) : 0;
+  const size_t b_stat = out->status ? al((size_t)ngal * nz) : 0;
+  const size_t b_i32 = al(sizeof(int32_t) * ngal), b_i64 = al(sizeof(int64_t) * ngal);
+  const size_t total = b_in + b_t + b_id + b_prof + b_scal + b_stat + 3 * b_i32 + b_i64;
+  if (total > c->stage_bytes) {
+    cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&c->d_stage, total));
+    c->stage_bytes = total;
+  }
+  unsigned char* p = (unsigned char*)c->d_stage;
+  double* d_in = (double*)p; p += b_in;
+  double* d_t = (double*)p; p += b_t;
+  int32_t* d_id = (int32_t*)p; p += b_id;
+  mag_outputs_t d;
+  d.profiles = out->profiles ? (double*)p : nullptr; p += b_prof;
+  d.scalars = out->scalars ? (double*)p : nullptr; p += b_scal;
+  d.status = out->status ? (char*)p : nullptr; p += b_stat;
+  d.nsteps = (int32_t*)p; p += b_i32;
+  d.error = (int32_t*)p; p += b_i32;
+  d.flags = (uint32_t*)p; p += b_i32;
+  d.point_stages = (int64_t*)p; p += b_i64;
+  cudaStream_t st = c->stream;
+  CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  CUDA_TRY(cudaMemcpyAsync(d_in, inputs, sizeof(double) * MAG_NINPUT * ngal * nz, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_t, t_gyr, sizeof(double) * nz, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_id, gal_ids, sizeof(int32_t) * ngal, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  int rc = launch_solve(c, ngal, d_id, nz, d_t, d_in, n_profile_q, profile_q, n_scalar_q, scalar_q, &d, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  if (out->profiles) CUDA_TRY(cudaMemcpyAsync(out->profiles, d.profiles, sizeof(double) * n_profile_q * ngal * nz * nr, cudaMemcpyDeviceToHost, st));
+  if (out->scalars) CUDA_TRY(cudaMemcpyAsync(out->scalars, d.scalars, sizeof(double) * n_scalar_q * ngal * nz, cudaMemcpyDeviceToHost, st));
+  if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)ngal * nz, cudaMemcpyDeviceToHost, st));
+  if (out->nsteps) CUDA_TRY(cudaMemcpyAsync(out->nsteps, d.nsteps, sizeof(int32_t) * ngal, cudaMemcpyDeviceToHost, st));
+  if (out->error) CUDA_TRY(cudaMemcpyAsync(out->error, d.error, sizeof(int32_t) * ngal, cudaMemcpyDeviceToHost, st));
+  if (out->flags) CUDA_TRY(cudaMemcpyAsync(out->flags, d.flags, sizeof(uint32_t) * ngal, cudaMemcpyDeviceToHost, st));
+  if (out->point_stages) CUDA_TRY(cudaMemcpyAsync(out->point_stages, d.point_stages, sizeof(int64_t) * ngal, cudaMemcpyDeviceToHost, st));
+  int fail = 0;
+  CUDA_TRY(cudaMemcpyAsync(&fail, c->d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->last_ms[2] = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms; c->last_ms[0] = 0;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[3] = ms;
+  if (fail) { set_error("grid extension beyond p_nx_MAX / workspace capacity (reference: stop, grid.f90:222-226)"); return fail; }
+  return MAG_OK;
+}
+
+int mag_last_timing(mag_ctx_t* c, double ms_out[4]) {
+  if (!c) return 0;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->last_ms[1] = ms;
+  for (int i = 0; i < 4; i++) ms_out[i] = c->last_ms[i];
+  return c->last_launches;
+}
+
+double mag_measure_fp64_peak(mag_ctx_t* c, int repeats) {
+  if (!c) return 0.0;
+  cudaSetDevice(c->device);
+  const int threads = 256, blocks = c->sm_count * 8, iters = 1 << 14;
+  double* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * threads * blocks) != cudaSuccess) return 0.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int r = 0; r < repeats + 1; r++) {
+    cudaEventRecord(e0, c->stream);
+    k_dfma_peak<<<blocks, threads, 0, c->stream>>>(d, iters);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * threads * blocks / (ms * 1e-3);
+    if (r > 0 && flops > best) best = flops;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return best;
+}
+
+// ---- test hooks (exported, not part of the reference-facing ABI)
+__global__ void k_test_bessel(const double* x, int n, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double i0, i1, k0, k1;
+  bessel_ik01(x[i], i0, i1, k0, k1);
+  out[i] = i0; out[n + i] = i1; out[2 * n + i] = k0; out[3 * n + i] = k1;
+}
+int mag_test_bessel(const double* x, int n, double* out /* [4][n] */) {
+  double *dx = nullptr, *dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dx, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&dout, sizeof(double) * 4 * n));
+  CUDA_TRY(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  k_test_bessel<<<(n + 127) / 128, 128>>>(dx, n, dout);
+  CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dout);
+  return MAG_OK;
+}
+__global__ void k_test_rng(int32_t igal, int32_t seed, int kind, int n, double* out) {
+  __shared__ RngState r;
+  if (threadIdx.x == 0) {
+    rng_seed(&r, igal, seed, kind);
+    for (int i = 0; i < n; i++) out[i] = rng_uniform_lane0(&r);
+  }
+}
+int mag_test_rng(int32_t igal, int32_t seed, int32_t kind, int32_t n, double* out) {
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * n));
+  k_test_rng<<<1, 32>>>(igal, seed, kind, n, d);
+  CUDA_TRY(cudaMemcpy(out, d, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return MAG_OK;
+}
+int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nxcap, use_fast */) {
+  if (!c) return MAG_ERR_BAD_ARGUMENT;
+  out[0] = c->sm_count; out[1] = c->ctas_per_sm; out[2] = c->nwarps; out[3] = c->nxcap; out[4] = c->use_fast;
+  return MAG_OK;
+}
+int mag_set_fast_path(mag_ctx_t* c, int32_t on) {
+  if (!c) return MAG_ERR_BAD_ARGUMENT;
+  c->use_fast = on ? 1 : 0;
+  return MAG_OK;
+}
+
+}  // extern "C"
