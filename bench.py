@@ -234,7 +234,8 @@ def run_b200(args):
             ora = oracle_lib.solve_batch(oracle_lib.default_params(), ids[:n], t, np.ascontiguousarray(inputs[:, :n]),
                                          profiles=PROFILES, scalars=SCALARS, nthreads=cores)
             cdt = time.perf_counter() - c0
-            from tests.parity import compare
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from parity import compare
             sub = {k: (v[:, :n] if k in ("profiles", "scalars") else v[:n]) if isinstance(v, np.ndarray) else v
                    for k, v in r.items()}
             rep = compare(sub, ora)

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.parity import compare
+from parity import compare
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
