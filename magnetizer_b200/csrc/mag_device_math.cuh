@@ -1,15 +1,18 @@
 // mag_device_math.cuh -- device-side numerics for the B200 dynamo kernels:
-// physical constants and code units (reference source/constants.f90), modified Bessel
-// functions (reference: GSL via source/bessel_functions.f90), the GSL root finders the
-// reference drives from source/root_finder.f90 (Brent bracket solver, secant +
-// central-difference fallback), libgfortran's RANDOM_NUMBER streams
-// (source/random.f90) and warp-level reductions.
+// physical constants and code units (reference source/constants.f90), the GSL root finders
+// the reference drives from source/root_finder.f90 (Brent bracket solver, secant +
+// central-difference fallback), libgfortran's RANDOM_NUMBER streams (source/random.f90)
+// and warp-level reductions.  Elementary functions: mag_det_math.cuh.
+//
+// This translation unit is compiled with --fmad=false: every expression outside the
+// explicit fma() calls of the hot loop is evaluated in source order with IEEE rounding,
+// which is what makes the root-finder decisions reproducible (see mag_det_math.cuh).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
-#include "mag_bessel_coeffs.cuh"
+#include "mag_det_math.cuh"
 
 namespace magdev {
 
@@ -77,64 +80,6 @@ __device__ __forceinline__ void warp_argmax_first(double& v, int& idx) {
     double ov = __shfl_xor_sync(FULL, v, o);
     int oi = __shfl_xor_sync(FULL, idx, o);
     if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
-}
-
-// ---------------------------------------------------------------- Bessel
-__device__ inline double cheb_eval(const double* c, int n, double t) {
-  // Clenshaw
-  double b1 = 0.0, b2 = 0.0;
-  const double t2 = 2.0 * t;
-  for (int k = n - 1; k >= 1; k--) {
-    double b0 = fma(t2, b1, c[k] - b2);
-    b2 = b1;
-    b1 = b0;
-  }
-  return fma(t, b1, c[0] - b2);
-}
-#define MAG_EULER 0.57721566490153286061
-
-// I0(x), I1(x), K0(x), K1(x) for x > 0, all four at once (the disk rotation curve needs
-// the combination I0 K0 - I1 K1, rotationCurves.f90:75-82)
-__device__ inline void bessel_ik01(double x, double& i0, double& i1, double& k0, double& k1) {
-  const double q = 0.25 * x * x;
-  if (x <= 8.0) {
-    double t0 = 1.0, s0 = 1.0, t1 = 1.0, s1 = 1.0;
-    for (int k = 1; k < 40; k++) {
-      t0 *= q / ((double)k * (double)k);
-      t1 *= q / ((double)k * (double)(k + 1));
-      s0 += t0;
-      s1 += t1;
-      if (t0 < 1e-18 * s0) break;
-    }
-    i0 = s0;
-    i1 = s1 * 0.5 * x;
-  } else {
-    const double t = 16.0 / x - 1.0;
-    const double e = exp(x) / sqrt(x);
-    i0 = e * cheb_eval(MAG_CHEB_I0, MAG_CHEB_I0_N, t);
-    i1 = e * cheb_eval(MAG_CHEB_I1, MAG_CHEB_I1_N, t);
-  }
-  if (x <= 2.0) {
-    const double lg = log(0.5 * x);
-    double t0 = 1.0, H = 0.0, s0 = 0.0;
-    double t1 = 1.0, psi1 = -MAG_EULER, psi2 = 1.0 - MAG_EULER, s1 = (psi1 + psi2);
-    for (int k = 1; k < 25; k++) {
-      t0 *= q / ((double)k * (double)k);
-      H += 1.0 / (double)k;
-      s0 += t0 * H;
-      t1 *= q / ((double)k * (double)(k + 1));
-      psi1 += 1.0 / (double)k;
-      psi2 += 1.0 / (double)(k + 1);
-      s1 += (psi1 + psi2) * t1;
-    }
-    k0 = -(lg + MAG_EULER) * i0 + s0;
-    k1 = 1.0 / x + lg * i1 - 0.25 * x * s1;
-  } else {
-    const double t = 4.0 / x - 1.0;
-    const double e = exp(-x) / sqrt(x);
-    k0 = e * cheb_eval(MAG_CHEB_K0, MAG_CHEB_K0_N, t);
-    k1 = e * cheb_eval(MAG_CHEB_K1, MAG_CHEB_K1_N, t);
   }
 }
 
@@ -232,7 +177,7 @@ __device__ inline double deriv_central(F f, double x, double h) {
   double error = round + trunc;
   if (round < trunc && (round > 0 && trunc > 0)) {
     double ro, roundo, trunco;
-    const double h_opt = h * pow(round / (2.0 * trunc), 1.0 / 3.0);
+    const double h_opt = h * detmath::det_pow(round / (2.0 * trunc), 1.0 / 3.0);
     central_deriv_(f, x, h_opt, &ro, &roundo, &trunco);
     const double error_opt = roundo + trunco;
     if (error_opt < error && fabs(ro - r0) < 4.0 * error) r0 = ro;
@@ -332,13 +277,13 @@ __device__ inline double rng_normal_lane0(RngState* r) {
   for (;;) {
     u = rng_uniform_lane0(r);
     v = rng_uniform_lane0(r);
-    v = __dmul_rn((double)1.7156f, v - 0.5);
+    v = (double)1.7156f * (v - 0.5);
     const double x = u - s;
     const double y = fabs(v) - t;
-    const double q = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dadd_rn(__dmul_rn(a, y), -__dmul_rn(b, x))));
+    const double q = x * x + y * (a * y - b * x);
     if (q < r1) break;
     if (q > r2) continue;
-    if (__dmul_rn(v, v) < __dmul_rn(__dmul_rn(-4.0, log(u)), __dmul_rn(u, u))) break;
+    if (v * v < -4.0 * detmath::det_log(u) * (u * u)) break;
   }
   return v / u;
 }

@@ -26,6 +26,8 @@ enum WsArray {
   A_OMK, A_GK, A_SIGD, A_SIGS, A_RM, A_RHO, A_HKPC, A_T0, A_T1, A_T2,
   // hoisted RHS coefficients (per snapshot)
   C_IR, C_C1, C_CA, C_CR, C_KDC, C_FB, C_P3, C_QC, C_W,
+  // folded coefficients of the register fast path (mag_rk_fast.cuh), zero at ghost points
+  C_W0, C_W1, C_W2, C_W3, C_W4, C_W5, C_W6, C_W0A, F_CA, F_GS, C_FBS, F_KDC, F_P3, F_QC, F_AK,
   A_COUNT
 };
 
@@ -46,6 +48,7 @@ struct KernelArgs {
   int32_t* counter;      // work queue head
   int32_t* fail;         // device-side error flag (nx overflow)
   int32_t use_fast;      // 1: use the register/smem fast path where it applies
+  int32_t* replays;      // diagnostic: fast-path blocks replayed with the generic path
 };
 
 // Per-warp scalar state.  Every lane holds an identical copy ("module variables" of the
@@ -212,13 +215,13 @@ __device__ inline double disk_omega(const RotCtx& c, double r) {
   const double rs = c.r_disk * MAG_DISK_SCALE_TO_HALFMASS;
   const double y = (fabs(r) > TOO_SMALL) ? fabs(r) / rs : TOO_SMALL / rs;
   double i0, i1, k0, k1;
-  bessel_ik01(y, i0, i1, k0, k1);
+  detmath::det_bessel_ik01(y, &i0, &i1, &k0, &k1);
   const double A = sqrt((i0 * k0 - i1 * k1) / c.disk_norm);
   return A * c.v_disk / c.r_disk;
 }
 __device__ inline double bulge_omega(const RotCtx& c, double r) {
   if (c.v_bulge < (double)1e-3f) return 0.0;
-  const double a_to_r50 = 0.41421356237309515;  // sqrt(2)-1 in double
+  const double a_to_r50 = sqrt(2.0) - 1.0;
   const double a = a_to_r50 * c.r_bulge;
   const double y = fabs(r) / a;
   const double y50 = 1.0 / a_to_r50;
@@ -228,7 +231,7 @@ __device__ inline double bulge_omega(const RotCtx& c, double r) {
 __device__ __forceinline__ double halo_velocity(const RotCtx& c, double r) {
   const double y = fabs(r) / c.r_halo;
   const double cy = c.halo_c * y;
-  const double B = (log(1.0 + cy) - cy / (1.0 + cy)) / y;
+  const double B = (detmath::det_log(1.0 + cy) - cy / (1.0 + cy)) / y;
   return sqrt(fabs(c.halo_A * B));
 }
 __device__ inline double halo_velocity_contracted(const RotCtx& c, double r, bool at_centre, uint32_t* flags) {
@@ -269,7 +272,7 @@ __device__ __forceinline__ double regularize_at(double rx, double r_xi, double O
     Omega = 0.0;
     k = 0.0;
   }
-  const double e = (k < (double)1e12f) ? exp(-k) : 0.0;
+  const double e = (k < (double)1e12f) ? detmath::det_exp(-k) : 0.0;
   return e * (Omega - Omega_xi) + Omega_xi;
 }
 
@@ -283,7 +286,7 @@ __device__ __forceinline__ double density_to_scaleheight(double h_d, double Sigm
   return Sigma_d * MAG_MSUN_SI / MAG_KPC_SI / MAG_KPC_SI / h_d / 2.0 / MAG_KPC_SI * 1e-3;
 }
 __device__ inline double exp_surface_density(double rs, double r, double M) {
-  return M / 2. / MAG_PI / (rs * rs) * exp(-r / rs);
+  return M / 2. / MAG_PI / (rs * rs) * detmath::det_exp(-r / rs);
 }
 __device__ inline double molecular_to_diffuse_ratio(const mag_params_t& P, double rdisk, double Sigma_g, double Sigma_star) {
   const double h_star_SI = P.p_stellarHeightToRadiusScale * MAG_DISK_SCALE_TO_HALFMASS * rdisk * MAG_KPC_SI;
@@ -293,7 +296,7 @@ __device__ inline double molecular_to_diffuse_ratio(const mag_params_t& P, doubl
   double v_star_SI = sqrt(MAG_PI * MAG_G_SI * h_star_SI * Ss);
   if (v_star_SI < v_gas_SI) v_star_SI = v_gas_SI;
   const double Pnot = MAG_PI / 2.0 * MAG_G_SI * Sg * (Sg + (v_gas_SI / v_star_SI) * Ss) * 10.0;
-  return pow(Pnot / P.p_Rmol_P0, P.p_Rmol_alpha);
+  return detmath::det_pow(Pnot / P.p_Rmol_P0, P.p_Rmol_alpha);
 }
 
 // The serial chain over radius, executed by lane 0 (bracket of radius i+1 comes from the
@@ -311,25 +314,39 @@ __device__ inline bool hydrostatic_chain_lane0(Gal& G, const double* r /*abs(r_k
   const double h_star = G.r_disk * MAG_DISK_SCALE_TO_HALFMASS * P.p_stellarHeightToRadiusScale;
   const double h_m = G.r_disk * MAG_DISK_SCALE_TO_HALFMASS * P.p_molecularHeightToRadiusScale;
   const double cs = P.p_ISM_sound_speed_km_s * 1e5;
+  // computes_midplane_ISM_pressure_from_B_and_rho with B = 0 (pressureEquilibrium.f90:561-573)
   const double Kgas = (P.p_ISM_kappa / 3.0 * (1. + 2. * P.p_ISM_xi) + 1.0 / P.p_ISM_gamma) * (cs * cs);
   const double kmkpc2 = (1e3 / MAG_KPC_SI) * (1e3 / MAG_KPC_SI);
   const bool use_bulge = P.p_use_Pbulge && G.Mstars_bulge > 1e3;
+  const bool use_dm = P.p_use_Pdm != 0;
   int error_count = 0;
   double minimum_h = 1e-3 * G.r_disk, maximum_h = 2.0 * G.r_disk, guess_h = (double)0.050f;
   bool gave_up = false;
   for (int i = ng + 2; i <= n && !gave_up; i++) {
     const int k = i - 1;
+    // pressure_equation (pressureEquilibrium.f90:262-311) = P1 + P2 - Pgas in the reference's
+    // operation order; only leading factors that the reference itself evaluates first are
+    // hoisted out of the root-finder iteration, so every residual is bit-identical to a
+    // literal evaluation (P2 is exactly -0 with p_enable_P2 = F)
     const double Sd_SI = Sigma_d[k] * MAG_MSUN_SI / MAG_KPC_SI / MAG_KPC_SI;
     const double Ss_SI = Sigma_star[k] * MAG_MSUN_SI / MAG_KPC_SI / MAG_KPC_SI;
     const double pre = MAG_PI * MAG_G_SI * Sd_SI * 10.0;
-    const double cA = pre * Sd_SI * 0.5;                 // Pd
-    const double cB = pre * Sd_SI * Rm[k];               // Pm / I_m
-    const double cC = pre * Ss_SI;                       // Pstars / I_stars
-    double cD = 0.0;                                     // (Pbulge + Pdm) / h
-    if (use_bulge) cD += Om_b[k] * (1.5 * Om_b[k] + G_b[k]) * kmkpc2 * Sd_SI * MAG_KPC_SI * 10.0;
-    if (P.p_use_Pdm) cD += Om_h[k] * (1.5 * Om_h[k] + G_h[k]) * kmkpc2 * Sd_SI * MAG_KPC_SI * 10.0;
-    const double cE = Kgas * density_to_scaleheight(1.0, Sigma_d[k]);  // Pgas * h
-    auto pe = [&](double h) { return cA + cB * (h / (h_m + h)) + cC * (h / (h_star + h)) + cD * h - cE / h; };
+    const double Pd = pre * Sd_SI * 1.0 * 0.5;
+    const double cPm = pre * Sd_SI * Rm[k];
+    const double cPs = pre * Ss_SI;
+    const double cPb = use_bulge ? Om_b[k] * (1.5 * Om_b[k] + G_b[k]) * kmkpc2 * Sd_SI : 0.0;
+    const double cPh = use_dm ? Om_h[k] * (1.5 * Om_h[k] + G_h[k]) * kmkpc2 * Sd_SI : 0.0;
+    auto pe = [&](double h) {
+      const double I_stars = h / (h_star + h);
+      const double I_m = h / (h_m + h);
+      const double Pm = cPm * I_m;
+      const double Pstars = cPs * I_stars;
+      const double Pbulge = use_bulge ? cPb * h * MAG_KPC_SI * 10.0 : 0.0;
+      const double Pdm = use_dm ? cPh * h * MAG_KPC_SI * 10.0 : 0.0;
+      const double P1 = Pd + Pm + Pstars + Pbulge + Pdm;
+      const double rho_cgs = Sd_SI / h / 2.0 / MAG_KPC_SI * 1e-3;
+      return P1 - Kgas * rho_cgs;
+    };
     const double pe_min = pe(minimum_h), pe_max = pe(maximum_h);
     double root = -17.0;
     if (signbit(pe_min) != signbit(pe_max)) {
@@ -340,9 +357,9 @@ __device__ inline bool hydrostatic_chain_lane0(Gal& G, const double* r /*abs(r_k
       if (!ok || root < 0) {
         if (error_count < 4 && i > ng + 2 + 2) {
           G.status = 'P';
-          double e = (log(h_d[k - 1]) - log(h_d[k - 2])) / (r[k - 1] - r[k - 2]) * (r[k] - r[k - 1]);
-          e = e + log(h_d[k - 1]);
-          root = exp(e);
+          double e = (detmath::det_log(h_d[k - 1]) - detmath::det_log(h_d[k - 2])) / (r[k - 1] - r[k - 2]) * (r[k] - r[k - 1]);
+          e = e + detmath::det_log(h_d[k - 1]);
+          root = detmath::det_exp(e);
           error_count++;
         } else {
           gave_up = true;
@@ -353,7 +370,7 @@ __device__ inline bool hydrostatic_chain_lane0(Gal& G, const double* r /*abs(r_k
     h_d[k] = root;
     rho_d[k] = density_to_scaleheight(root, Sigma_d[k]);
     if (i != n) {
-      guess_h = root * exp((r[k + 1] - r[k]) / rs);
+      guess_h = root * detmath::det_exp((r[k + 1] - r[k]) / rs);
       maximum_h = guess_h * (1.0 + 25.0 / 100.);
       minimum_h = guess_h * (1.0 - 25.0 / 100.);
     }
@@ -394,10 +411,10 @@ __device__ inline bool construct_profiles(Gal& G) {
   c.f_b = (G.Mstars_disk + G.Mstars_bulge + G.Mgas_disk) / G.Mhalo;
   {
     double i0, i1, k0, k1;
-    bessel_ik01(1.0 / MAG_DISK_SCALE_TO_HALFMASS, i0, i1, k0, k1);
+    detmath::det_bessel_ik01(1.0 / MAG_DISK_SCALE_TO_HALFMASS, &i0, &i1, &k0, &k1);
     c.disk_norm = i0 * k0 - i1 * k1;
     c.halo_c = 1.0 / G.nfw_cs1;
-    c.halo_A = G.v_halo * G.v_halo / (log(1.0 + c.halo_c) - c.halo_c / (1.0 + c.halo_c));
+    c.halo_A = G.v_halo * G.v_halo / (detmath::det_log(1.0 + c.halo_c) - c.halo_c / (1.0 + c.halo_c));
   }
   const bool with_halo = G.is_central || !P.p_ignore_satellite_DM_haloes;
   const double rreg = P.p_rreg_to_rdisk * G.r_disk;
@@ -543,7 +560,7 @@ __device__ inline bool construct_profiles(Gal& G) {
       const double kD = Gc[i] * (hi * hi * hi) / (et * et);
       cKDC[i] = kD / pi2_5;
       const double Ncells = fabs(3.0 * r * Dr * hi / (li * li * li) / lam2);
-      const double b = exp(-Dr / 2. / fabs(r)) * (P.fmag * be) / sqrt(Ncells) * li / Dr * lam / 3 * P.C_floor;
+      const double b = detmath::det_exp(-Dr / 2. / fabs(r)) * (P.fmag * be) / sqrt(Ncells) * li / Dr * lam / 3 * P.C_floor;
       cFB[i] = (pi2 * pi2) * et / (hi * hi) * b;
       const double lkr = 1.0 / lk[i];
       cP3[i] = -2 * (lkr * lkr) * et / (be * be);

@@ -215,7 +215,7 @@ struct mag_ctx {
   int nwarps = 0;
   int nxcap = 0;
   double* ws = nullptr;
-  int* d_counter = nullptr;  // [0] queue head, [1] fail flag
+  int* d_counter = nullptr;  // [0] queue head, [1] fail flag, [2] fast-path replays
   int* d_hist = nullptr;
   int* d_key = nullptr;
   int* d_order = nullptr;
@@ -303,7 +303,7 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   c->nxcap = (cap + 15) & ~15;
   CUDA_TRY(cudaMalloc(&c->ws, (size_t)c->nwarps * A_COUNT * c->nxcap * sizeof(double)));
   CUDA_TRY(cudaMemset(c->ws, 0, (size_t)c->nwarps * A_COUNT * c->nxcap * sizeof(double)));
-  CUDA_TRY(cudaMalloc(&c->d_counter, 2 * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_counter, 4 * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->d_hist, 4096 * sizeof(int)));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
@@ -340,7 +340,7 @@ static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int3
     c->order_cap = ngal;
   }
   int launches = 0;
-  CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, (nz + 1) * sizeof(int), st));
   const int tb = 256, gb = (ngal + tb - 1) / tb;
   k_cost_hist<<<gb, tb, 0, st>>>(d_inputs /* column 0 = r_disk */, ngal, nz, c->P.p_rdisk_min, c->d_key, c->d_hist);
@@ -360,6 +360,7 @@ static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int3
   a.ws = c->ws; a.nxcap = c->nxcap;
   a.counter = c->d_counter; a.fail = c->d_counter + 1;
   a.use_fast = c->use_fast;
+  a.replays = c->d_counter + 2;
   int ctas = c->sm_count * c->ctas_per_sm;
   const int need = (ngal + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   if (need < ctas) ctas = need;
@@ -481,7 +482,7 @@ __global__ void k_test_bessel(const double* x, int n, double* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double i0, i1, k0, k1;
-  bessel_ik01(x[i], i0, i1, k0, k1);
+  detmath::det_bessel_ik01(x[i], &i0, &i1, &k0, &k1);
   out[i] = i0; out[n + i] = i1; out[2 * n + i] = k0; out[3 * n + i] = k1;
 }
 int mag_test_bessel(const double* x, int n, double* out /* [4][n] */) {
@@ -492,6 +493,24 @@ int mag_test_bessel(const double* x, int n, double* out /* [4][n] */) {
   k_test_bessel<<<(n + 127) / 128, 128>>>(dx, n, dout);
   CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
   cudaFree(dx); cudaFree(dout);
+  return MAG_OK;
+}
+__global__ void k_test_det(int which, int n, const double* x, const double* y, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = which == 0 ? detmath::det_log(x[i]) : which == 1 ? detmath::det_exp(x[i]) : detmath::det_pow(x[i], y[i]);
+}
+// elementary functions of mag_det_math.cuh: 0 log, 1 exp, 2 pow(x,y)
+int mag_test_det_math(int32_t which, int32_t n, const double* x, const double* y, double* out) {
+  double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dx, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&dy, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&dout, sizeof(double) * n));
+  CUDA_TRY(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+  k_test_det<<<(n + 127) / 128, 128>>>(which, n, dx, dy, dout);
+  CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dy); cudaFree(dout);
   return MAG_OK;
 }
 __global__ void k_test_rng(int32_t igal, int32_t seed, int kind, int n, double* out) {
@@ -509,9 +528,12 @@ int mag_test_rng(int32_t igal, int32_t seed, int32_t kind, int32_t n, double* ou
   cudaFree(d);
   return MAG_OK;
 }
-int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nxcap, use_fast */) {
+int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nxcap, use_fast, replays of the last solve */) {
   if (!c) return MAG_ERR_BAD_ARGUMENT;
   out[0] = c->sm_count; out[1] = c->ctas_per_sm; out[2] = c->nwarps; out[3] = c->nxcap; out[4] = c->use_fast;
+  out[5] = 0;
+  cudaSetDevice(c->device);
+  cudaMemcpy(&out[5], c->d_counter + 2, sizeof(int), cudaMemcpyDeviceToHost);
   return MAG_OK;
 }
 int mag_set_fast_path(mag_ctx_t* c, int32_t on) {

@@ -84,9 +84,10 @@ class DynamoSolver:
 
     # -- diagnostics ---------------------------------------------------------
     def info(self):
-        out = (C.c_int32 * 5)()
+        out = (C.c_int32 * 6)()
         _check(self._lib.mag_ctx_info(self._ctx, out), "mag_ctx_info")
-        return dict(sm_count=out[0], ctas_per_sm=out[1], nwarps=out[2], nxcap=out[3], use_fast=out[4])
+        return dict(sm_count=out[0], ctas_per_sm=out[1], nwarps=out[2], nxcap=out[3], use_fast=out[4],
+                    fast_path_replays=out[5])
 
     def set_fast_path(self, on: bool):
         _check(self._lib.mag_set_fast_path(self._ctx, C.c_int32(1 if on else 0)), "mag_set_fast_path")

@@ -263,7 +263,7 @@ struct Galaxy {
       q = xq * xq + y * (a * y - b * xq);
       if (q < r1) break;
       if (q > r2) continue;
-      if (vv * vv < -4.0 * std::log(u) * (u * u)) break;
+      if (vv * vv < -4.0 * m_log(u) * (u * u)) break;
     }
     return vv / u;
   }
@@ -495,8 +495,8 @@ struct Galaxy {
   double halo_velocity(double r) const {
     double y = std::fabs(r) / r_halo;
     double c = 1.0 / nfw_cs1;
-    double A = v_halo * v_halo / (std::log(1.0 + c) - c / (1.0 + c));
-    double B = (std::log(1.0 + c * y) - c * y / (1.0 + c * y)) / y;
+    double A = v_halo * v_halo / (m_log(1.0 + c) - c / (1.0 + c));
+    double B = (m_log(1.0 + c * y) - c * y / (1.0 + c * y)) / y;
     double v2 = A * B;
     return std::sqrt(std::fabs(v2));
   }
@@ -524,11 +524,14 @@ struct Galaxy {
       return halo_velocity(r);
     }
     int i;
+    double p15 = 1.0;  // 1.5d0**i: exact in binary floating point for i <= 11
     for (i = 1; i <= 10; i++) {
-      if (fun(r * std::pow(1.5, i)) / fun_min < 0) break;
+      p15 *= 1.5;
+      if (fun(r * p15) / fun_min < 0) break;
     }
+    if (i > 10) p15 *= 1.5;  // loop index after a completed DO loop is 11
     double r0;
-    bool ok = find_root_brent(fun, r, r * std::pow(1.5, i), &r0);
+    bool ok = find_root_brent(fun, r, r * p15, &r0);
     if (!ok) {
       // reference: error_message(abort=.true.) -> MPI_ABORT.  Propagate as NaN.
       return std::numeric_limits<double>::quiet_NaN();
@@ -551,7 +554,7 @@ struct Galaxy {
         Omega[i] = 0.0;
         rxi_over_r_k = 0.0;
       }
-      if (rxi_over_r_k < (double)1e12f) e = std::exp(-rxi_over_r_k); else e = 0;
+      if (rxi_over_r_k < (double)1e12f) e = m_exp(-rxi_over_r_k); else e = 0;
       Omega[i] = e * (Omega[i] - Omega_xi) + Omega_xi;
     }
   }
@@ -559,7 +562,7 @@ struct Galaxy {
   // -------------------------------------------------------------- surface_density.f90
   // exp_surface_density, :26-38
   static double exp_surface_density(double rs, double r, double M) {
-    return M / 2. / pi / (rs * rs) * std::exp(-r / rs);
+    return M / 2. / pi / (rs * rs) * m_exp(-r / rs);
   }
   // midplane_pressure_Elmegreen, :86-128 and molecular_to_diffuse_ratio, :69-83
   double molecular_to_diffuse_ratio(double rdisk, double Sigma_g, double Sigma_star) const {
@@ -571,7 +574,7 @@ struct Galaxy {
     if (v_star_SI < v_gas_SI) v_star_SI = v_gas_SI;
     double Pnot = pi / 2.0 * G_SI * Sigma_g_SI * (Sigma_g_SI + (v_gas_SI / v_star_SI) * Sigma_star_SI) *
                   convertPressureSItoGaussian;
-    return std::pow(Pnot / P.p_Rmol_P0, P.p_Rmol_alpha);
+    return m_pow(Pnot / P.p_Rmol_P0, P.p_Rmol_alpha);
   }
 
   // -------------------------------------------------------------- pressureEquilibrium.f90
@@ -671,9 +674,9 @@ struct Galaxy {
         if (!success || h_d[k] < 0) {
           if (error_count < ERROR_COUNT_MAX && i > nghost_actual + 2 + 2) {
             status_code = 'P';
-            h_d[k] = (std::log(h_d[k - 1]) - std::log(h_d[k - 2])) / (r[k - 1] - r[k - 2]) * (r[k] - r[k - 1]);
-            h_d[k] = h_d[k] + std::log(h_d[k - 1]);
-            h_d[k] = std::exp(h_d[k]);
+            h_d[k] = (m_log(h_d[k - 1]) - m_log(h_d[k - 2])) / (r[k - 1] - r[k - 2]) * (r[k] - r[k - 1]);
+            h_d[k] = h_d[k] + m_log(h_d[k - 1]);
+            h_d[k] = m_exp(h_d[k]);
             error_count = error_count + 1;
           } else {
             for (int j = 0; j < n_; j++) { h_d[j] = -1; rho_d[j] = 0.0; }
@@ -683,7 +686,7 @@ struct Galaxy {
       }
       rho_d[k] = density_to_scaleheight(h_d[k], Sigma_d[k]);
       if (i != n_) {
-        guess_h = h_d[k] * std::exp((r[k + 1] - r[k]) / rs);
+        guess_h = h_d[k] * m_exp((r[k + 1] - r[k]) / rs);
         maximum_h = guess_h * (1.0 + GUESS_INTERVAL / 100.);
         minimum_h = guess_h * (1.0 - GUESS_INTERVAL / 100.);
       }
@@ -821,7 +824,7 @@ struct Galaxy {
       double r = x[i];
       double Ncells = std::fabs(3.0 * r * Delta_r * h[i] / (l[i] * l[i] * l[i]) / (lambda * lambda));
       double brms = P.fmag * Beq[i];
-      double b = std::exp(-Delta_r / 2. / std::fabs(r)) * brms / std::sqrt(Ncells) * l[i] / Delta_r * lambda / 3;
+      double b = m_exp(-Delta_r / 2. / std::fabs(r)) * brms / std::sqrt(Ncells) * l[i] / Delta_r * lambda / 3;
       B_floor[i] = b * Bfloor_sign * P.C_floor;
     }
     if ((int)sign_array.size() != nx) refresh_sign_array = true;
@@ -1229,6 +1232,14 @@ void oracle_rng_normals(int32_t gal_id, int32_t p_random_seed, int32_t kind, int
   oracle::Galaxy g(p);
   g.set_random_seed(gal_id, p_random_seed);
   for (int i = 0; i < n; i++) out[i] = g.random_normal();
+}
+// elementary functions of det_math.hpp: 0 log, 1 exp, 2 pow(x,y)
+void oracle_det_math(int32_t which, int32_t n, const double* x, const double* y, double* out) {
+  for (int i = 0; i < n; i++)
+    out[i] = which == 0 ? detmath::det_log(x[i]) : which == 1 ? detmath::det_exp(x[i]) : detmath::det_pow(x[i], y[i]);
+}
+void oracle_bessel_all(int32_t n, const double* x, double* out /* [4][n] */) {
+  for (int i = 0; i < n; i++) detmath::det_bessel_ik01(x[i], out + i, out + n + i, out + 2 * n + i, out + 3 * n + i);
 }
 double oracle_bessel(int32_t which, double x) {
   switch (which) {

@@ -22,7 +22,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("magnetizer_oracle.cpp", "oracle_numerics.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("magnetizer_oracle.cpp", "oracle_numerics.hpp", "det_math.hpp", "bessel_coeffs.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "magnetizer_b200.h"))
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)

@@ -12,8 +12,8 @@
 //     xoshiro256** for GCC >= 9, xorshift1024* for GCC 7/8
 //     (libgfortran/intrinsics/random.c).  Call sites: source/random.f90:39,64,90-91,126.
 //   * modified Bessel functions I0,I1,K0,K1 (gsl_sf_bessel_*; call sites
-//     source/bessel_functions.f90:33-69): libstdc++ std::cyl_bessel_i/k are used; any
-//     implementation accurate to ~1e-15 is sufficient for the 1e-8 parity target.
+//     source/bessel_functions.f90:33-69) and libm's log/exp/pow: pinned deterministic
+//     implementations in det_math.hpp (which explains why library calls cannot be used).
 //
 // PARITY UNPINNED against the real reference: the reference cannot be built in this
 // image (no gfortran/MPI/HDF5/GSL/FGSL) and its own tests pin no number.  What IS
@@ -25,6 +25,8 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+
+#include "det_math.hpp"
 
 namespace oracle {
 
@@ -203,7 +205,7 @@ double deriv_central(F&& f, double x, double h) {
   error = round + trunc;
   if (round < trunc && (round > 0 && trunc > 0)) {
     double r_opt, round_opt, trunc_opt, error_opt;
-    double h_opt = h * std::pow(round / (2.0 * trunc), 1.0 / 3.0);
+    double h_opt = h * detmath::det_pow(round / (2.0 * trunc), 1.0 / 3.0);
     central_deriv_(f, x, h_opt, &r_opt, &round_opt, &trunc_opt);
     error_opt = round_opt + trunc_opt;
     if (error_opt < error && std::fabs(r_opt - r_0) < 4.0 * error) {
@@ -257,9 +259,13 @@ bool find_root_secant(F&& f, double guess, double step, double* root_out) {
 }
 
 // ---------------------------------------------------------------- Bessel ----
-inline double bessel_I0(double x) { return std::cyl_bessel_i(0.0, x); }
-inline double bessel_I1(double x) { return std::cyl_bessel_i(1.0, x); }
-inline double bessel_K0(double x) { return std::cyl_bessel_k(0.0, x); }
-inline double bessel_K1(double x) { return std::cyl_bessel_k(1.0, x); }
+// det_math.hpp explains why these are pinned implementations rather than library calls
+inline double bessel_I0(double x) { double a, b, c, d; detmath::det_bessel_ik01(x, &a, &b, &c, &d); return a; }
+inline double bessel_I1(double x) { double a, b, c, d; detmath::det_bessel_ik01(x, &a, &b, &c, &d); return b; }
+inline double bessel_K0(double x) { double a, b, c, d; detmath::det_bessel_ik01(x, &a, &b, &c, &d); return c; }
+inline double bessel_K1(double x) { double a, b, c, d; detmath::det_bessel_ik01(x, &a, &b, &c, &d); return d; }
+inline double m_log(double x) { return detmath::det_log(x); }
+inline double m_exp(double x) { return detmath::det_exp(x); }
+inline double m_pow(double x, double y) { return detmath::det_pow(x, y); }
 
 }  // namespace oracle

@@ -38,14 +38,36 @@ def test_device_rng_matches_libgfortran_golden(solver):
             assert rc == 0 and np.array_equal(got, want), case["igal"]
 
 
-def test_device_bessel_matches_oracle(solver, oracle):
-    xs = np.concatenate([np.geomspace(1e-7, 2, 200), np.linspace(2, 40, 400)])
-    got = np.empty((4, xs.size))
-    assert solver._lib.mag_test_bessel(xs.ctypes.data_as(C.c_void_p), C.c_int(xs.size), got.ctypes.data_as(C.c_void_p)) == 0
-    L = oracle.lib()
-    for which in range(4):
-        want = np.array([L.oracle_bessel(which, float(x)) for x in xs])
-        assert np.max(np.abs(got[which] / want - 1)) < 5e-14, which
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_device_bessel_bit_exact(solver, oracle):
+    """I0, I1, K0, K1: the device twin of oracle/det_math.hpp returns identical bits."""
+    xs = np.concatenate([np.geomspace(1e-7, 2, 2000), np.linspace(2, 40, 4000)])
+    got, want = np.empty((4, xs.size)), np.empty((4, xs.size))
+    assert solver._lib.mag_test_bessel(_vp(xs), C.c_int(xs.size), _vp(got)) == 0
+    oracle.lib().oracle_bessel_all(C.c_int32(xs.size), _vp(xs), _vp(want))
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_device_det_math_bit_exact(solver, oracle):
+    """log, exp, pow on 3e5 arguments each: bit-identical on the device and in the oracle
+    (the Brent decisions of the profile solves depend on the last bit, oracle/det_math.hpp)."""
+    rng = np.random.default_rng(11)
+    n = 300000
+    cases = [
+        (0, np.concatenate([np.exp(rng.uniform(-700, 700, n - 4)), [1.0, 0.5, 1e-310, 2.0]]), None),
+        (1, np.concatenate([rng.uniform(-745, 709, n // 2), rng.uniform(-2, 2, n // 2)]), None),
+        (2, np.exp(rng.uniform(-40, 40, n)), rng.uniform(-3, 3, n)),
+    ]
+    for which, x, y in cases:
+        x = np.ascontiguousarray(x)
+        y = np.ascontiguousarray(y if y is not None else x)
+        got, want = np.empty_like(x), np.empty_like(x)
+        assert solver._lib.mag_test_det_math(C.c_int32(which), C.c_int32(x.size), _vp(x), _vp(y), _vp(got)) == 0
+        oracle.lib().oracle_det_math(C.c_int32(which), C.c_int32(x.size), _vp(x), _vp(y), _vp(want))
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), which
 
 
 def test_single_galaxy_mode(solver, oracle, example_input):
@@ -79,6 +101,7 @@ def test_example_full_run(solver, oracle, example_input):
     ora = oracle.solve_batch(solver.params, ids, t, inputs)
     rep = compare(gpu, ora)
     print("worst row-relative errors:", {k: f"{v:.2e}" for k, v in rep.items() if v > 0})
+    print("fast-path blocks replayed:", solver.info()["fast_path_replays"])
 
 
 def test_generic_path_agrees_with_fast_path(solver, oracle, example_input):

@@ -123,3 +123,29 @@ def test_constants(oracle):
     assert p.p_ISM_turbulent_length == float(np.float32(0.1))
     assert p.p_stellarHeightToRadiusScale == 1.0 / float(np.float32(7.3))
     assert p.p_nx_ref == 101 and p.p_nsteps_max == 20000 and p.p_random_seed == 17
+
+
+def test_det_math_accuracy_against_host_libm(oracle):
+    """oracle/det_math.hpp: log and exp within 1 ulp of the host libm, pow within 2e-14
+    relative (the reference's libm is unpinned; see the header for why these are pinned)."""
+    L = oracle.lib()
+    rng = np.random.default_rng(5)
+
+    def call(which, x, y=None):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.ascontiguousarray(y if y is not None else x, np.float64)
+        out = np.empty_like(x)
+        L.oracle_det_math(C.c_int32(which), C.c_int32(x.size), x.ctypes.data_as(C.c_void_p),
+                          y.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 50000)), rng.uniform(0.5, 2, 50000), [2.0, 0.5, 1e-310]])
+    got, want = call(0, x), np.log(x)
+    assert np.max(np.abs(got - want) / np.spacing(np.abs(want))) <= 1.0
+    assert call(0, np.array([1.0]))[0] == 0.0 and call(0, np.array([0.0]))[0] == -np.inf
+    x = np.concatenate([rng.uniform(-745, 709, 50000), rng.uniform(-1, 1, 50000)])
+    got, want = call(1, x), np.exp(x)
+    assert np.max(np.abs(got - want) / np.spacing(want)) <= 1.0
+    x, y = np.exp(rng.uniform(-30, 30, 50000)), rng.uniform(-3, 3, 50000)
+    assert np.max(np.abs(call(2, x, y) / np.power(x, y) - 1)) < 2e-14
+    assert call(2, np.array([0.0]), np.array([0.92]))[0] == 0.0
