@@ -257,7 +257,6 @@ __device__ __noinline__ bool run_timesteps_fast(Gal& G, RkShared* rs) {
   const int nx = G.nx, lane = G.lane, m = nx - MAG_NGHOST - 1;
   const int npts = 32 * PPL;
   const double Rk = G.a->P.R_kappa;
-  if (G.refresh_sign || G.sign_nx != nx) refresh_signs(G);   // first pde call of the attempt
   prepare_fast_coefs(G, npts);
   const GuardK gk = guard_constants(G);
 
@@ -354,20 +353,26 @@ __device__ __noinline__ bool run_timesteps_fast(Gal& G, RkShared* rs) {
     }
     const double ck_t = G.t, ck_tl = G.t_last_sign_choice;
     const bool ck_refresh = G.refresh_sign;
-    if (lane < 18) ((uint64_t*)&rs->rng_ck)[lane] = ((const uint64_t*)&rs->rng)[lane];
+    const int ck_sign_nx = G.sign_nx;
+    static_assert(sizeof(RngState) == 17 * sizeof(uint64_t), "RngState layout");
+    if (lane < 17) ((uint64_t*)&rs->rng_ck)[lane] = ((const uint64_t*)&rs->rng)[lane];
     bool signs_saved = false;
     unsigned mB = 0, mA = 0;
     publish(buf);
     for (int s = 0; s < nb; s++) {
       const double this_t = G.t_Gyr + dtg * (double)(jt + s);
-      if (floor_sign_due(G, this_t)) {
-        if (!signs_saved) {  // first flip of the block: keep the old signs for a replay
+      // same order of RNG draws as the reference: update_floor_sign (dynamo.f90:196-198) may
+      // draw Bfloor_sign, then the first pde of the step redraws the layer signs if flagged
+      // or if the grid size changed (floor_field.f90:55-79)
+      update_floor_sign(G, this_t);
+      if (G.refresh_sign || G.sign_nx != nx) {
+        if (!signs_saved) {  // first refresh of the block: keep the old signs for a replay
           const double* sg = G.A(A_SIGN); double* bk = G.A(A_OMK);
-          for (int i = lane; i < nx; i += 32) bk[i] = sg[i];
+          const int nsave = max(nx, ck_sign_nx);
+          for (int i = lane; i < nsave; i += 32) bk[i] = sg[i];
           signs_saved = true;
           __syncwarp();
         }
-        update_floor_sign(G, this_t);
         refresh_signs(G);
         load_signed_floor();
       }
@@ -403,16 +408,16 @@ __device__ __noinline__ bool run_timesteps_fast(Gal& G, RkShared* rs) {
     }
     if (signs_saved) {
       double* sg = G.A(A_SIGN); const double* bk = G.A(A_OMK);
-      for (int i = lane; i < nx; i += 32) sg[i] = bk[i];
+      const int nsave = max(nx, ck_sign_nx);
+      for (int i = lane; i < nsave; i += 32) sg[i] = bk[i];
     }
-    if (lane < 18) ((uint64_t*)&rs->rng)[lane] = ((const uint64_t*)&rs->rng_ck)[lane];
-    G.t = ck_t; G.t_last_sign_choice = ck_tl; G.refresh_sign = ck_refresh;
+    if (lane < 17) ((uint64_t*)&rs->rng)[lane] = ((const uint64_t*)&rs->rng_ck)[lane];
+    G.t = ck_t; G.t_last_sign_choice = ck_tl; G.refresh_sign = ck_refresh; G.sign_nx = ck_sign_nx;
     __syncwarp();
     impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
     if (!run_steps_generic(G, jt, nb)) return false;
     jt += nb;
-    if (G.refresh_sign || G.sign_nx != nx) refresh_signs(G);
-    load_signed_floor();
+    load_signed_floor();   // (a refresh still pending after the replay happens at the next step)
     load_state();
   }
   // ---- hand the state back to the workspace (the caller applies impose_bc)
