@@ -19,6 +19,9 @@
 
 namespace magdev {
 
+struct SnapRec;
+struct GalHead;
+
 // ------------------------------------------------------------------ workspace
 enum WsArray {
   A_X = 0, A_RKPC, A_H, A_N, A_L, A_LKPC, A_ETAT, A_TAU, A_BEQ, A_ALPK, A_OM, A_G, A_OMD, A_OMB, A_OMH, A_GB, A_GH,
@@ -43,13 +46,23 @@ struct KernelArgs {
   int32_t profile_q[MAG_NPROFILE];
   int32_t scalar_q[MAG_NSCALAR];
   mag_outputs_t out;
-  double* ws;            // [nwarps][A_COUNT][nxcap]
+  int32_t g0, g1;        // galaxy range of this chunk
+  double* ws;            // Phase A: [nwarps][A_COUNT][nxcap]
+  double* ws2;           // Phase B: [nteams][A_COUNT][nxcap]
   int32_t nxcap;
-  int32_t* counter;      // work queue head
+  int32_t* counter;      // Phase A work queue head
+  int32_t* counter2;     // Phase B work queue head
   int32_t* fail;         // device-side error flag (nx overflow)
   int32_t use_fast;      // 1: use the register/smem fast path where it applies
   int32_t* replays;      // diagnostic: fast-path blocks replayed with the generic path
+  // snapshot records exchanged between the profile phase and the evolve phase (mag_phases.cuh)
+  SnapRec* recs;         // [ngal][nz]
+  GalHead* heads;        // [ngal]
+  double* arena;         // record arrays
+  unsigned long long* arena_top;
+  long long arena_cap;   // in doubles
 };
+#define MAG_ERR_ARENA (-6)  // internal: record arena exhausted (the host retries with smaller chunks)
 
 // Per-warp scalar state.  Every lane holds an identical copy ("module variables" of the
 // reference: input_params, grid, floor_field, messages::status_code).
@@ -593,63 +606,59 @@ __device__ inline void set_timestep(Gal& G, bool have_profiles) {
   if (G.nsteps > P.p_nsteps_max) G.nsteps = P.p_nsteps_max;
 }
 
-// adjust_grid (grid.f90:143-297), default switches.  Returns false on nx overflow.
-__device__ inline bool adjust_grid(Gal& G) {
+// adjust_grid (grid.f90:143-297), default switches -- the GRID part (x, r_kpc, dx, dr_kpc,
+// r_max_kpc, lambda, nx), which depends on the r_disk history only.  Reports what the
+// reference does to the field array so that the evolve phase can repeat it on f:
+// *nx_mid = grid size after the optional scale-back (== nx before it if none),
+// *scaled / *extended = which of the two f transformations happen.
+// Returns false on nx overflow (reference: stop, grid.f90:222-226).
+__device__ inline bool adjust_grid_geometry(Gal& G, int* nx_mid, bool* scaled, bool* extended) {
   const mag_params_t& P = G.a->P;
   const double GRID_ADJ_THRES = (double)0.05f;
   const int nx_def = P.p_nx_ref + 2 * MAG_NGHOST, lane = G.lane, ng = MAG_NGHOST;
   double *x = G.A(A_X), *rk = G.A(A_RKPC);
-  double *f[3] = {G.A(A_F0), G.A(A_F1), G.A(A_F2)};
-  double *tmp[4] = {G.A(A_T0), G.A(A_T1), G.A(A_T2), G.A(A_P0)};
+  double* tmp = G.A(A_T0);
+  *scaled = false; *extended = false;
   if (G.nx != nx_def) {  // scale back to the default resolution
     const int nx_old = G.nx;
-    for (int i = lane; i < nx_old; i += 32) { tmp[0][i] = rk[i]; tmp[1][i] = f[0][i]; tmp[2][i] = f[1][i]; tmp[3][i] = f[2][i]; }
+    for (int i = lane; i < nx_old; i += 32) tmp[i] = rk[i];
     __syncwarp();
     G.nx = nx_def;
     const int n_old = nx_old - ng, n_new = nx_def - ng;
-    for (int i = lane; i < n_new; i += 32) {
-      rk[ng + i] = rescale_at(tmp[0] + ng, n_old, i, n_new);
-      f[0][ng + i] = rescale_at(tmp[1] + ng, n_old, i, n_new);
-      f[1][ng + i] = rescale_at(tmp[2] + ng, n_old, i, n_new);
-      f[2][ng + i] = rescale_at(tmp[3] + ng, n_old, i, n_new);
-    }
-    if (lane < ng) { f[0][lane] = 0.0; f[1][lane] = 0.0; f[2][lane] = 0.0; }
+    for (int i = lane; i < n_new; i += 32) rk[ng + i] = rescale_at(tmp + ng, n_old, i, n_new);
     __syncwarp();
-    G.dr_kpc = __dadd_rn(rk[ng + 1], -rk[ng]);
-    if (lane == 0) for (int i = ng; i >= 1; i--) rk[i - 1] = __dadd_rn(rk[i], -G.dr_kpc);
+    G.dr_kpc = rk[ng + 1] - rk[ng];
+    if (lane == 0) for (int i = ng; i >= 1; i--) rk[i - 1] = rk[i] - G.dr_kpc;
     __syncwarp();
     for (int i = lane; i < G.nx; i += 32) x[i] = rk[i] / G.r_max_kpc;
     __syncwarp();
+    *scaled = true;
     // dx is NOT updated here
   }
+  *nx_mid = G.nx;
   const double prev = G.r_max_kpc;
-  G.r_max_kpc = __dmul_rn(P.p_rmax_over_rdisk, G.r_disk);
+  G.r_max_kpc = P.p_rmax_over_rdisk * G.r_disk;
   const double relvar = fabs(G.r_max_kpc - prev) / prev;
   if (relvar < GRID_ADJ_THRES) { G.r_max_kpc = prev; return true; }
   if (G.r_max_kpc >= prev) {
     int nx_new = G.nx;
     double cand = prev;
-    const double base = __dadd_rn(MAG_R_IN / G.dx, -(double)ng);
+    const double base = MAG_R_IN / G.dx - (double)ng;
     while (cand < G.r_max_kpc) {
       nx_new += 1;
-      cand = __dmul_rn(__dadd_rn(base, __dadd_rn((double)(nx_new - ng), -1.0)), G.dr_kpc);
+      cand = (base + ((double)(nx_new - ng) - 1.0)) * G.dr_kpc;
       if (nx_new > P.p_nx_MAX + 1) break;
     }
     if (nx_new > P.p_nx_MAX || nx_new > G.a->nxcap) return false;
     G.r_max_kpc = cand;
     const int nx = G.nx;
-    if (lane == 0) for (int i = nx; i <= nx_new; i++) rk[i - 1] = __dadd_rn(rk[i - 2], G.dr_kpc);
+    if (lane == 0) for (int i = nx; i <= nx_new; i++) rk[i - 1] = rk[i - 2] + G.dr_kpc;
     __syncwarp();
     for (int i = lane; i < nx_new; i += 32) x[i] = rk[i] / G.r_max_kpc;
     __syncwarp();
-    G.dx = __dadd_rn(x[1], -x[0]);
-    const int keep = nx - ng - 1;  // f(:nx-nxghost-1,:) kept
-    for (int v = 0; v < 3; v++) {
-      const double edge = f[v][keep - 1];
-      __syncwarp();
-      for (int i = nx - ng - 1 + lane; i < nx_new; i += 32) f[v][i] = edge * rk[keep - 1] / rk[i];
-    }
+    G.dx = x[1] - x[0];
     G.nx = nx_new;
+    *extended = true;
     __syncwarp();
   } else {
     const double dr_new = G.dr_kpc * G.r_max_kpc / prev;
@@ -659,6 +668,39 @@ __device__ inline bool adjust_grid(Gal& G) {
   }
   G.lambda = 1.0 / G.r_max_kpc;
   return true;
+}
+
+// The FIELD part of adjust_grid.  Scale-back (grid.f90:167-193 -> rescale_f_array,
+// interpolation.f90:170-198): the interior of every column is resampled linearly from
+// nx_old-3 to nx_def-3 points; the inner ghost zone is left for impose_bc.
+__device__ inline void adjust_f_scaleback(Gal& G, int nx_old, int nx_def) {
+  const int lane = G.lane, ng = MAG_NGHOST;
+  double *f[3] = {G.A(A_F0), G.A(A_F1), G.A(A_F2)};
+  double *tmp[3] = {G.A(A_T0), G.A(A_T1), G.A(A_T2)};
+  for (int i = lane; i < nx_old; i += 32) { tmp[0][i] = f[0][i]; tmp[1][i] = f[1][i]; tmp[2][i] = f[2][i]; }
+  __syncwarp();
+  const int n_old = nx_old - ng, n_new = nx_def - ng;
+  for (int i = lane; i < n_new; i += 32) {
+    f[0][ng + i] = rescale_at(tmp[0] + ng, n_old, i, n_new);
+    f[1][ng + i] = rescale_at(tmp[1] + ng, n_old, i, n_new);
+    f[2][ng + i] = rescale_at(tmp[2] + ng, n_old, i, n_new);
+  }
+  if (lane < ng) { f[0][lane] = 0.0; f[1][lane] = 0.0; f[2][lane] = 0.0; }
+  __syncwarp();
+}
+// Extension (grid.f90:262-276): points up to nx-nxghost-1 are kept, the rest follows 1/r.
+// rk = r_kpc of the EXTENDED grid (its first nx points are the old grid).
+__device__ inline void adjust_f_extend(Gal& G, int nx, int nx_new) {
+  const int lane = G.lane, ng = MAG_NGHOST;
+  const double* rk = G.A(A_RKPC);
+  const int keep = nx - ng - 1;  // f(:nx-nxghost-1,:) kept
+  for (int v = 0; v < 3; v++) {
+    double* f = G.A(A_F0 + v);
+    const double edge = f[keep - 1];
+    __syncwarp();
+    for (int i = nx - ng - 1 + lane; i < nx_new; i += 32) f[i] = edge * rk[keep - 1] / rk[i];
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ floor field signs
@@ -816,7 +858,33 @@ __device__ inline const double* profile_source(const Gal& G, int q) {
   }
 }
 
-__device__ inline void make_ts_arrays(Gal& G, int it) {
+// true for the quantities whose rows the evolve phase writes (they depend on f); all other
+// profiles depend on the ISM profiles only and are written by the profile phase
+__device__ __forceinline__ bool is_field_quantity(int q) {
+  return q == MAG_Q_BR || q == MAG_Q_BP || q == MAG_Q_ALP_M || q == MAG_Q_BZMOD || q == MAG_Q_ALP;
+}
+
+// make_ts_arrays (ts_arrays.f90:76-203), rows of snapshot `it` that depend on the ISM profiles only
+__device__ inline void write_profile_rows(Gal& G, int it) {
+  const KernelArgs* a = G.a;
+  const int nr = a->P.p_nx_ref, ni = G.nx - 2 * MAG_NGHOST, ng = MAG_NGHOST, lane = G.lane;
+  const int nz = a->nz, ngal = a->ngal, g = G.g;
+  if (a->out.profiles) {
+    for (int qq = 0; qq < a->n_profile_q; qq++) {
+      const int q = a->profile_q[qq];
+      if (is_field_quantity(q)) continue;
+      const double* src = profile_source(G, q);
+      double* dst = a->out.profiles + (((size_t)qq * ngal + g) * nz + (it - 1)) * nr;
+      const double cval = (q == MAG_Q_V) ? G.v_code : 0.0;
+      for (int i = lane; i < nr; i += 32) dst[i] = src ? rescale_at(src + ng, ni, i, nr) : cval;
+    }
+  }
+  __syncwarp();
+}
+
+// make_ts_arrays, rows that depend on the field: Br, Bp, alp_m, Bzmod, alp, the scalars and
+// the status character
+__device__ inline void write_field_rows(Gal& G, int it) {
   const KernelArgs* a = G.a;
   const int nr = a->P.p_nx_ref, ni = G.nx - 2 * MAG_NGHOST, ng = MAG_NGHOST, lane = G.lane;
   const int nz = a->nz, ngal = a->ngal, g = G.g;
@@ -825,12 +893,11 @@ __device__ inline void make_ts_arrays(Gal& G, int it) {
   if (a->out.profiles) {
     for (int qq = 0; qq < a->n_profile_q; qq++) {
       int q = a->profile_q[qq];
+      if (!is_field_quantity(q)) continue;
       if (q == MAG_Q_ALP && !alp_ok) q = MAG_Q_H;  // ts_arrays.f90:200-201: stale tmp (= h)
       const double* src = profile_source(G, q);
       double* dst = a->out.profiles + (((size_t)qq * ngal + g) * nz + (it - 1)) * nr;
-      double cval = 0.0;
-      if (q == MAG_Q_V) cval = G.v_code;
-      for (int i = lane; i < nr; i += 32) dst[i] = src ? rescale_at(src + ng, ni, i, nr) : cval;
+      for (int i = lane; i < nr; i += 32) dst[i] = rescale_at(src + ng, ni, i, nr);
     }
   }
   if (a->out.scalars && a->n_scalar_q > 0) {

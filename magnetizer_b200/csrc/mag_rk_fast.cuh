@@ -1,12 +1,13 @@
 // mag_rk_fast.cuh -- the time-stepping loop of one snapshot (dynamo.f90:168-212):
 // nsteps x { update_floor_sign ; rk (3 stages, gutsdynamo.f90:404-448) ; impose_bc }.
 //
-// Register-resident fast path.  Lane l of the warp owns PPL consecutive radial points
-// (4l .. 4l+3 for PPL = 4, nx <= 128): the state f = (Br, Bp, alp_m), the 2N-storage
-// register ftmp and -- for PPL = 4 -- all per-point coefficients stay in registers for the
-// whole snapshot.  Per stage each lane publishes its points to a double-buffered
-// shared-memory line, reads the 3+3 halo points of its neighbours after ONE __syncwarp,
-// and evaluates the RHS in a folded form:
+// Register-resident fast path on a TEAM of 64 threads (2 warps, one CTA) per galaxy.
+// Thread t owns PPL consecutive radial points (2t, 2t+1 for PPL = 2, nx <= 128): the state
+// f = (Br, Bp, alp_m), the 2N-storage register ftmp and the per-point coefficients stay in
+// registers for the whole snapshot (PPL = 2), or the 7 stencil weights come from shared
+// memory (PPL = 3, 4: nx <= 192, 256).  Per stage each thread publishes its points to a
+// double-buffered shared-memory line, reads the 3+3 halo points of its neighbours after ONE
+// CTA barrier, and evaluates the RHS in a folded form:
 //
 //   L(f)_i   = sum_k w_k(i) f_{i+k}            7 per-point weights = cr*(xder2 + xder/r - 1/r^2) - c1
 //   dBr/dt   = L(Br) - ca*alp*Bp
@@ -21,39 +22,57 @@
 // check_f_error (gutsdynamo.f90:450-463) is evaluated by the reference after every stage on
 // ALL points including ghost zones and the r = 0 point, whose values are one-sided-stencil
 // garbage that impose_bc resets.  The fast path evaluates exact values only where the
-// reference uses centred stencils on meaningful data; every BLK steps it reduces a running
-// maximum and accepts the block only if a rigorous bound on the garbage points stays below
-// the blow-up thresholds.  Otherwise the block is replayed from a checkpoint with the
-// generic path (mag_galaxy.cuh), which evaluates every point exactly like the reference --
-// so status codes, RNG draw order and the accumulated time stay exact.
+// reference uses centred stencils on meaningful data; every BLK steps it reduces running
+// maxima and accepts the block only if (a) no exactly evaluated value crossed a threshold and
+// (b) a rigorous bound on the garbage points -- which depend on the 7 points next to each
+// boundary only -- stays below the thresholds.  Otherwise the block is replayed from a
+// checkpoint with the generic path (mag_galaxy.cuh), which evaluates every point exactly
+// like the reference, so status codes, RNG draw order and the accumulated time stay exact.
 #pragma once
-#include "mag_galaxy.cuh"
+#include "mag_phases.cuh"
 
 namespace magdev {
 
 #define MAG_FAST_BLK 8        // steps per checkpoint block
-#define MAG_FAST_MAXPPL 8     // shared line sized for nx <= 256
+#define MAG_TEAM 64           // threads per galaxy team
+#define MAG_FAST_MAXPPL 4     // shared line sized for nx <= 256
 
-// per-warp shared memory
+// parameters of one fast-loop call, written by the leader warp, read by both
+struct FastCall {
+  double* W;            // team workspace
+  int32_t nxcap, nx, nsteps, ppl;
+  int32_t sign_nx, refresh_sign, cmd, ok;
+  double dt, t, t_Gyr, dtg, tau_min_kappa, t_last_sign_choice, Rk;
+  long long point_stages;
+};
+#define TEAM_CMD_FAST 1
+#define TEAM_CMD_EXIT 2
+
+struct GuardK {
+  double kb_lin, kb_a, fb0, fbk, akmax, ka_lin, kp, kq;
+};
+
+// per-team shared memory
 struct RkShared {
   RngState rng;
-  RngState rng_ck;                                 // checkpoint copy
-  double line[2][3][MAG_FAST_MAXPPL * 32];         // [buffer][variable][slot*32 + lane]
+  RngState rng_ck;                                        // checkpoint copy
+  FastCall call;
+  GuardK gk[2];
+  unsigned red[8];                                        // block maxima (high words)
+  double line[2][3][MAG_FAST_MAXPPL * MAG_TEAM];          // [buffer][variable][slot*64 + thread]
+  double wts[8][MAG_FAST_MAXPPL * MAG_TEAM];              // stencil weights for PPL >= 3
 };
 
 // update_floor_sign (floor_field.f90:99-114)
-__device__ __forceinline__ bool floor_sign_due(const Gal& G, double time) {
-  return time - G.t_last_sign_choice > G.a->P.p_floor_kappa * G.tau_min;
-}
 __device__ __forceinline__ void update_floor_sign(Gal& G, double time) {
-  if (floor_sign_due(G, time)) {
+  if (time - G.t_last_sign_choice > G.a->P.p_floor_kappa * G.tau_min) {
     (void)random_sign(G);  // Bfloor_sign: its square cancels in the target field
     G.t_last_sign_choice = time;
     G.refresh_sign = true;
   }
 }
 
-// nb steps of the generic path (exact reference semantics).  Returns ok.
+// nb steps of the generic path (exact reference semantics), leader warp only.  Returns ok.
 __device__ __noinline__ bool run_steps_generic(Gal& G, int jt0, int nb) {
   const double dtg = G.dt * G.a->U.t0_Gyr;
   for (int jt = jt0; jt < jt0 + nb; jt++) {
@@ -66,8 +85,8 @@ __device__ __noinline__ bool run_steps_generic(Gal& G, int jt0, int nb) {
   return true;
 }
 
-// ---- folded coefficients of one snapshot, written to the workspace for g in [0, 32*PPL)
-// (zeros at ghost and unused points, so that those slots stay inert)
+// ---- folded coefficients of one snapshot, written to the workspace for g in [0, npts)
+// (zeros at ghost and unused points, so that those slots stay inert).  Leader warp.
 __device__ __noinline__ void prepare_fast_coefs(Gal& G, int npts) {
   const int nx = G.nx, m = nx - MAG_NGHOST - 1;
   const double* x = G.A(A_X);
@@ -103,11 +122,9 @@ __device__ __noinline__ void prepare_fast_coefs(Gal& G, int npts) {
 }
 
 // ---- rigorous bound on the values check_f_error sees at the points the fast path does not
-// evaluate exactly (6 ghost points with one-sided stencils, Br/Bp at the r = 0 point)
-struct GuardK {
-  double kb_lin, kb_a, fb0, fbk, akmax, ka_lin, kp, kq;
-};
-__device__ __noinline__ GuardK guard_constants(Gal& G) {
+// evaluate exactly: side 0 = the 3 inner ghost points and Br/Bp at the r = 0 point (their
+// stencils read points 0..6), side 1 = the 3 outer ghost points (points nx-7..nx-1)
+__device__ __noinline__ void guard_constants(Gal& G, GuardK* out /* [2], shared memory */) {
   const int nx = G.nx;
   const double* x = G.A(A_X);
   const double ddx = x[1] - x[0];
@@ -115,92 +132,113 @@ __device__ __noinline__ GuardK guard_constants(Gal& G) {
   const double *cIR = G.A(C_IR), *cC1 = G.A(C_C1), *cCA = G.A(C_CA), *cCR = G.A(C_CR), *cKDC = G.A(C_KDC);
   const double *cFB = G.A(C_FB), *cP3 = G.A(C_P3), *cQC = G.A(C_QC), *cW = G.A(C_W), *Gc = G.A(A_G), *ak = G.A(A_ALPK);
   const double Rk = fabs(G.a->P.R_kappa);
-  GuardK k = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (G.lane < 7) {
-    // lanes 0-2: left ghosts, 3-5: right ghosts, 6: the r = 0 point
-    const int g = G.lane < 3 ? G.lane : (G.lane < 6 ? nx - 6 + G.lane : MAG_NGHOST);
-    const double ir = fabs(cIR[g]), cr = fabs(cCR[g]);
-    if (G.lane < 6) {
-      k.kb_lin = fabs(cC1[g]) + cr * (ir * ir + S1 * ir + S2) + fabs(Gc[g]);
-      k.ka_lin = fabs(cW[g]) + Rk * cr * (S2 + S1 * ir);
-    } else {
-      // Br = Bp = 0 at the centre when pde is evaluated: only the derivative terms survive
-      k.kb_lin = cr * (110.0 / (60. * ddx) * ir + 1078.0 / (180. * (ddx * ddx))) + fabs(Gc[g]);
-      k.ka_lin = 0.0;  // alp_m at the centre is evaluated exactly
+  for (int side = 0; side < 2; side++) {
+    GuardK k = {0, 0, 0, 0, 0, 0, 0, 0};
+    // side 0: lanes 0-2 inner ghosts, lane 3 the centre; side 1: lanes 0-2 outer ghosts
+    const bool active = side == 0 ? G.lane < 4 : G.lane < 3;
+    if (active) {
+      const int g = side == 0 ? G.lane : nx - 3 + G.lane;
+      const double ir = fabs(cIR[g]), cr = fabs(cCR[g]);
+      if (!(side == 0 && G.lane == 3)) {
+        k.kb_lin = fabs(cC1[g]) + cr * (ir * ir + S1 * ir + S2) + fabs(Gc[g]);
+        k.ka_lin = fabs(cW[g]) + Rk * cr * (S2 + S1 * ir);
+        k.kp = fabs(cP3[g]);
+        k.kq = fabs(cP3[g] * cQC[g]);
+      } else {
+        // Br = Bp = 0 at the centre when pde is evaluated: only the derivative terms survive;
+        // alp_m at the centre is evaluated exactly
+        k.kb_lin = cr * (110.0 / (60. * ddx) * ir + 1078.0 / (180. * (ddx * ddx))) + fabs(Gc[g]);
+      }
+      k.kb_a = fabs(cCA[g]);
+      k.fb0 = fabs(cFB[g]);
+      k.fbk = fabs(cFB[g] * cKDC[g]);
+      k.akmax = fabs(ak[g]);
     }
-    k.kb_a = fabs(cCA[g]);
-    k.fb0 = fabs(cFB[g]);
-    k.fbk = fabs(cFB[g] * cKDC[g]);
-    k.akmax = fabs(ak[g]);
-    k.kp = G.lane < 6 ? fabs(cP3[g]) : 0.0;
-    k.kq = G.lane < 6 ? fabs(cP3[g] * cQC[g]) : 0.0;
+    k.kb_lin = warp_max(k.kb_lin); k.kb_a = warp_max(k.kb_a); k.fb0 = warp_max(k.fb0); k.fbk = warp_max(k.fbk);
+    k.akmax = warp_max(k.akmax); k.ka_lin = warp_max(k.ka_lin); k.kp = warp_max(k.kp); k.kq = warp_max(k.kq);
+    if (G.lane == 0) out[side] = k;
   }
-  k.kb_lin = warp_max(k.kb_lin); k.kb_a = warp_max(k.kb_a); k.fb0 = warp_max(k.fb0); k.fbk = warp_max(k.fbk);
-  k.akmax = warp_max(k.akmax); k.ka_lin = warp_max(k.ka_lin); k.kp = warp_max(k.kp); k.kq = warp_max(k.kq);
-  return k;
+  __syncwarp();
 }
-// true when no point of the reference's f can have crossed the check_f_error thresholds
-__device__ __forceinline__ bool guard_ok(const GuardK& k, double dt, double MB, double MA) {
+// true when the garbage points of one side cannot have crossed the check_f_error thresholds;
+// MB / MA bound |Br|,|Bp| / |alp_m| on the 7 points next to that boundary during the block
+__device__ __forceinline__ bool guard_side_ok(const GuardK& k, double dt, double MB, double MA) {
   const double A = k.akmax + MA;
   const double bB = MB + 4.0 * dt * (MB * (k.kb_lin + k.kb_a * A) + k.fb0 + k.fbk * A);
   const double bA = MA + 4.0 * dt * (k.kp * A * 2.0 * MB * MB + k.kq * sqrt(A) * MB * MB + k.ka_lin * MA);
   return (bB < 1e8) && (bA < 1000.0);   // false for NaN
 }
 
-template <int PPL, bool COEF_REGS>
+// sqrt|x| for the quenching term: MUFU.RSQ64H seed + coupled Newton (Goldschmidt) steps,
+// branch free; |x| is clamped away from 0/denormals (the term it multiplies is then < 1e-150)
+__device__ __forceinline__ double fast_sqrt_abs(double x) {
+  int hi = __double2hiint(x) & 0x7fffffff;
+  hi = max(hi, 0x00200000);
+  x = __hiloint2double(hi, __double2loint(x));
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r, h = 0.5 * r;
+  double e = fma(-g, h, 0.5);
+  g = fma(g, e, g); h = fma(h, e, h);
+  e = fma(-g, h, 0.5);
+  g = fma(g, e, g); h = fma(h, e, h);
+  e = fma(-g, g, x);           // final correction: g += (x - g^2) * h
+  return fma(e, h, g);
+}
+
+template <int PPL, bool W_SMEM>
 struct FastState {
   double f[3][PPL], ft[3][PPL];
-  // coefficients (registers when COEF_REGS, else re-read from the workspace every stage)
-  double w[COEF_REGS ? PPL : 1][7], w0a[COEF_REGS ? PPL : 1], ca[COEF_REGS ? PPL : 1], gs[COEF_REGS ? PPL : 1];
-  double fb[COEF_REGS ? PPL : 1], kdc[COEF_REGS ? PPL : 1], p3[COEF_REGS ? PPL : 1], qc[COEF_REGS ? PPL : 1];
-  double ak[COEF_REGS ? PPL : 1];
+  double w[W_SMEM ? 1 : PPL][7], w0a[W_SMEM ? 1 : PPL];
+  double ca[PPL], gs[PPL], fb[PPL], kdc[PPL], p3[PPL], qc[PPL], ak[PPL];
 };
 
+// address (slot*64 + thread) of the halo point at distance d (-3..-1, PPL..PPL+2) from this
+// thread's first point
+template <int PPL>
+__device__ __forceinline__ int halo_addr(int tid, int d) {
+  const int dthr = (d >= 0) ? d / PPL : -((-d + PPL - 1) / PPL);
+  const int slot = d - dthr * PPL;
+  return slot * MAG_TEAM + ((tid + dthr) & (MAG_TEAM - 1));
+}
+
 // One Runge-Kutta stage.  STAGE: 0,1,2.  Reads the halo from line `buf`, updates f/ft in
-// registers, publishes the new f to the other line.  mB/mA: running maxima of the high words of
-// |Br|,|Bp| and |alp_m| over this lane's live points.
-template <int PPL, bool COEF_REGS, int STAGE>
-__device__ __forceinline__ void fast_stage(FastState<PPL, COEF_REGS>& S, const Gal& G, double (*line)[3][MAG_FAST_MAXPPL * 32],
-                                           int buf, double dg, double dz, double Rk, uint32_t pub_mask, uint32_t zero_mask,
-                                           uint32_t mir_mask, const int* mir_addr, bool reload, unsigned& mB, unsigned& mA,
-                                           bool write_alp) {
-  const int lane = G.lane;
-  const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
-  __syncwarp();
+// registers, publishes the new state (boundary conditions applied) to the other line.
+template <int PPL, bool W_SMEM, int STAGE>
+__device__ __forceinline__ void fast_stage(FastState<PPL, W_SMEM>& S, RkShared* rs, int tid, int buf, double dg, double dz,
+                                           double Rk, uint32_t pub_mask, uint32_t zero_mask, uint32_t mir_mask,
+                                           uint32_t near_mask, const int* mir_addr, bool reload, unsigned& mB, unsigned& mA,
+                                           unsigned& nB, unsigned& nA, double* alp_out) {
+  __syncthreads();
   // ---- gather the window: PPL own points + 3 halo points each side
   double win[3][PPL + 6];
 #pragma unroll
   for (int v = 0; v < 3; v++) {
-    const double* L = line[buf][v];
+    const double* L = rs->line[buf][v];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      win[v][k] = (lane == 0) ? 0.0 : L[(PPL - 3 + k) * 32 + lm];
-      win[v][PPL + 3 + k] = (lane == 31) ? 0.0 : L[k * 32 + lp];
+      win[v][k] = L[halo_addr<PPL>(tid, k - 3)];
+      win[v][PPL + 3 + k] = L[halo_addr<PPL>(tid, PPL + k)];
     }
-    if (reload) {  // lanes that own ghost / Dirichlet points take the boundary-conditioned values
+    if (reload) {  // threads that own ghost / Dirichlet points take the boundary-conditioned values
 #pragma unroll
-      for (int j = 0; j < PPL; j++) S.f[v][j] = L[j * 32 + lane];
+      for (int j = 0; j < PPL; j++) S.f[v][j] = L[j * MAG_TEAM + tid];
     }
 #pragma unroll
     for (int j = 0; j < PPL; j++) win[v][3 + j] = S.f[v][j];
   }
   // ---- RHS and update, point by point
-  const int g0 = lane * PPL;
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
-    double w[7], w0a, ca, gs, fb, kdc, p3, qc, ak;
-    if (COEF_REGS) {
+    double w[7], w0a;
+    if (W_SMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) w[k] = S.w[COEF_REGS ? j : 0][k];
-      w0a = S.w0a[COEF_REGS ? j : 0]; ca = S.ca[COEF_REGS ? j : 0]; gs = S.gs[COEF_REGS ? j : 0];
-      fb = S.fb[COEF_REGS ? j : 0]; kdc = S.kdc[COEF_REGS ? j : 0]; p3 = S.p3[COEF_REGS ? j : 0];
-      qc = S.qc[COEF_REGS ? j : 0]; ak = S.ak[COEF_REGS ? j : 0];
+      for (int k = 0; k < 7; k++) w[k] = rs->wts[k][j * MAG_TEAM + tid];
+      w0a = rs->wts[7][j * MAG_TEAM + tid];
     } else {
-      const int g = g0 + j;
 #pragma unroll
-      for (int k = 0; k < 7; k++) w[k] = G.A(C_W0 + k)[g];
-      w0a = G.A(C_W0A)[g]; ca = G.A(F_CA)[g]; gs = G.A(F_GS)[g]; fb = G.A(C_FBS)[g]; kdc = G.A(F_KDC)[g];
-      p3 = G.A(F_P3)[g]; qc = G.A(F_QC)[g]; ak = G.A(F_AK)[g];
+      for (int k = 0; k < 7; k++) w[k] = S.w[W_SMEM ? 0 : j][k];
+      w0a = S.w0a[W_SMEM ? 0 : j];
     }
     const double Br = win[0][3 + j], Bp = win[1][3 + j], am = win[2][3 + j];
     double LBr = w[0] * win[0][j], LBp = w[0] * win[1][j], Lam = w[0] * win[2][j];
@@ -210,13 +248,13 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, COEF_REGS>& S, const G
       LBp = fma(w[k], win[1][j + k], LBp);
       if (k != 3) Lam = fma(w[k], win[2][j + k], Lam);
     }
-    const double a = ak + am;
-    if (write_alp) G.A(A_ALP)[g0 + j] = a;
-    const double p0 = fma(-(ca * a), Bp, LBr);
-    const double p1 = fma(fb, fma(kdc, a, 1.0), fma(gs, Br, LBp));
+    const double a = S.ak[j] + am;
+    if (alp_out) alp_out[tid * PPL + j] = a;
+    const double p0 = fma(-(S.ca[j] * a), Bp, LBr);
+    const double p1 = fma(S.fb[j], fma(S.kdc[j], a, 1.0), fma(S.gs[j], Br, LBp));
     const double B2 = fma(Br, Br, Bp * Bp);
-    const double em = fma(qc * sqrt(fabs(a)) * Br, Bp, a * B2);
-    const double p2 = fma(p3, em, fma(Rk, Lam, w0a * am));
+    const double em = fma(S.qc[j] * fast_sqrt_abs(a) * Br, Bp, a * B2);
+    const double p2 = fma(S.p3[j], em, fma(Rk, Lam, w0a * am));
     const double b0 = (STAGE == 0) ? Br : S.ft[0][j];
     const double b1 = (STAGE == 0) ? Bp : S.ft[1][j];
     const double b2 = (STAGE == 0) ? am : S.ft[2][j];
@@ -225,48 +263,58 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, COEF_REGS>& S, const G
     if (STAGE < 2) {
       S.ft[0][j] = fma(dz, p0, n0); S.ft[1][j] = fma(dz, p1, n1); S.ft[2][j] = fma(dz, p2, n2);
     }
-    mB = max(mB, (unsigned)__double2hiint(n0) & 0x7fffffffu);
-    mB = max(mB, (unsigned)__double2hiint(n1) & 0x7fffffffu);
+    mB = max(mB, max((unsigned)__double2hiint(n0) & 0x7fffffffu, (unsigned)__double2hiint(n1) & 0x7fffffffu));
     mA = max(mA, (unsigned)__double2hiint(n2) & 0x7fffffffu);
   }
   // ---- publish the new state with boundary conditions applied
-  double (*Ln)[MAG_FAST_MAXPPL * 32] = line[buf ^ 1];
+  double (*Ln)[MAG_FAST_MAXPPL * MAG_TEAM] = rs->line[buf ^ 1];
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
     if (pub_mask & (1u << j)) {
       const bool z = zero_mask & (1u << j);
-      Ln[0][j * 32 + lane] = z ? 0.0 : S.f[0][j];
-      Ln[1][j * 32 + lane] = z ? 0.0 : S.f[1][j];
-      Ln[2][j * 32 + lane] = S.f[2][j];
+      Ln[0][j * MAG_TEAM + tid] = z ? 0.0 : S.f[0][j];
+      Ln[1][j * MAG_TEAM + tid] = z ? 0.0 : S.f[1][j];
+      Ln[2][j * MAG_TEAM + tid] = S.f[2][j];
     }
   }
-  if (mir_mask) {
+  if (near_mask) {  // the few threads next to a boundary
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
       if (mir_mask & (1u << j)) {
         const int a = mir_addr[j];
         Ln[0][a] = -S.f[0][j]; Ln[1][a] = -S.f[1][j]; Ln[2][a] = S.f[2][j];
+        nB = max(nB, max((unsigned)__double2hiint(S.f[0][j]) & 0x7fffffffu, (unsigned)__double2hiint(S.f[1][j]) & 0x7fffffffu));
       }
+      if (near_mask & (1u << j)) nA = max(nA, (unsigned)__double2hiint(S.f[2][j]) & 0x7fffffffu);
     }
   }
 }
 
-// Fast time loop for one snapshot attempt.  Returns ok (false: check_f_error tripped).
-template <int PPL, bool COEF_REGS>
-__device__ __noinline__ bool run_timesteps_fast(Gal& G, RkShared* rs) {
-  const int nx = G.nx, lane = G.lane, m = nx - MAG_NGHOST - 1;
-  const int npts = 32 * PPL;
-  const double Rk = G.a->P.R_kappa;
-  prepare_fast_coefs(G, npts);
-  const GuardK gk = guard_constants(G);
+// Fast time loop of one snapshot attempt, executed by all 64 threads of the team.  G is the
+// leader warp's galaxy state (nullptr in the helper warp).  The result is left in rs->call
+// (ok, t, t_last_sign_choice, sign_nx, refresh_sign, point_stages) and in the workspace.
+template <int PPL, bool W_SMEM>
+__device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
+  const int tid = threadIdx.x;
+  const bool leader = tid < 32;
+  const FastCall C = rs->call;
+  double* const W = C.W;
+  const int nxcap = C.nxcap, nx = C.nx, m = nx - MAG_NGHOST - 1, nsteps = C.nsteps;
+  const int npts = MAG_TEAM * PPL;
+  const double Rk = C.Rk, dt = C.dt;
+  auto WA = [&](int id) { return W + (size_t)id * nxcap; };
 
-  // per-lane publishing tables: which slots are published / zeroed / mirrored into a ghost slot
-  uint32_t pub_mask = 0, zero_mask = 0, mir_mask = 0;
+  if (leader) { prepare_fast_coefs(*G, npts); guard_constants(*G, rs->gk); }
+  __syncthreads();
+
+  // per-thread publishing tables: which slots are published / zeroed / mirrored into a ghost slot
+  uint32_t pub_mask = 0, zero_mask = 0, mir_mask = 0, near_mask = 0;
   int mir_addr[PPL];
   bool reload = false;
+  int side = -1;
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
-    const int g = lane * PPL + j;
+    const int g = tid * PPL + j;
     mir_addr[j] = 0;
     const bool ghost = (g < MAG_NGHOST) || (g > m && g < nx);
     if (!ghost) pub_mask |= 1u << j;                       // ghost slots are written by their mirror source
@@ -274,56 +322,56 @@ __device__ __noinline__ bool run_timesteps_fast(Gal& G, RkShared* rs) {
     int dst = -1;
     if (g > MAG_NGHOST && g <= 2 * MAG_NGHOST) dst = 2 * MAG_NGHOST - g;          // 4,5,6 -> 2,1,0
     if (g < m && g >= m - MAG_NGHOST) dst = 2 * m - g;                            // m-1.. -> m+1..
-    if (dst >= 0) { mir_mask |= 1u << j; mir_addr[j] = (dst % PPL) * 32 + dst / PPL; }
+    if (dst >= 0) { mir_mask |= 1u << j; mir_addr[j] = (dst % PPL) * MAG_TEAM + dst / PPL; }
+    if (dst >= 0 || g == MAG_NGHOST || g == m) { near_mask |= 1u << j; side = (g <= 2 * MAG_NGHOST) ? 0 : 1; }
     if (ghost || g == MAG_NGHOST || g == m) reload = true;
   }
 
-  FastState<PPL, COEF_REGS> S;
+  FastState<PPL, W_SMEM> S;
   auto load_state = [&]() {
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
-      const int g = lane * PPL + j;
+      const int g = tid * PPL + j;
       const bool in = g < nx;
 #pragma unroll
-      for (int v = 0; v < 3; v++) { S.f[v][j] = in ? G.A(A_F0 + v)[g] : 0.0; S.ft[v][j] = 0.0; }
+      for (int v = 0; v < 3; v++) { S.f[v][j] = in ? WA(A_F0 + v)[g] : 0.0; S.ft[v][j] = 0.0; }
     }
   };
   auto load_signed_floor = [&]() {
-    const double *cFB = G.A(C_FB), *sg = G.A(A_SIGN);
-    double* fbs = G.A(C_FBS);
+    const double *cFB = WA(C_FB), *sg = WA(A_SIGN);
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
-      const int g = lane * PPL + j;
-      const double v = (g >= MAG_NGHOST && g <= m) ? sg[g] * cFB[g] : 0.0;
-      if (COEF_REGS) S.fb[COEF_REGS ? j : 0] = v; else fbs[g] = v;
+      const int g = tid * PPL + j;
+      S.fb[j] = (g >= MAG_NGHOST && g <= m) ? sg[g] * cFB[g] : 0.0;
     }
-    __syncwarp();
   };
-  if (COEF_REGS) {
 #pragma unroll
-    for (int j = 0; j < PPL; j++) {
-      const int g = lane * PPL + j;
+  for (int j = 0; j < PPL; j++) {
+    const int g = tid * PPL + j;
+    if (W_SMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) S.w[COEF_REGS ? j : 0][k] = G.A(C_W0 + k)[g];
-      S.w0a[COEF_REGS ? j : 0] = G.A(C_W0A)[g]; S.ca[COEF_REGS ? j : 0] = G.A(F_CA)[g];
-      S.gs[COEF_REGS ? j : 0] = G.A(F_GS)[g]; S.kdc[COEF_REGS ? j : 0] = G.A(F_KDC)[g];
-      S.p3[COEF_REGS ? j : 0] = G.A(F_P3)[g]; S.qc[COEF_REGS ? j : 0] = G.A(F_QC)[g];
-      S.ak[COEF_REGS ? j : 0] = G.A(F_AK)[g];
+      for (int k = 0; k < 7; k++) rs->wts[k][j * MAG_TEAM + tid] = WA(C_W0 + k)[g];
+      rs->wts[7][j * MAG_TEAM + tid] = WA(C_W0A)[g];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 7; k++) S.w[W_SMEM ? 0 : j][k] = WA(C_W0 + k)[g];
+      S.w0a[W_SMEM ? 0 : j] = WA(C_W0A)[g];
     }
+    S.ca[j] = WA(F_CA)[g]; S.gs[j] = WA(F_GS)[g]; S.kdc[j] = WA(F_KDC)[g];
+    S.p3[j] = WA(F_P3)[g]; S.qc[j] = WA(F_QC)[g]; S.ak[j] = WA(F_AK)[g];
   }
   load_signed_floor();
   load_state();
 
-  // publish the initial state (boundary conditions applied) into line 0
   auto publish = [&](int buf) {
-    double (*Ln)[MAG_FAST_MAXPPL * 32] = rs->line[buf];
+    double (*Ln)[MAG_FAST_MAXPPL * MAG_TEAM] = rs->line[buf];
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
       if (pub_mask & (1u << j)) {
         const bool z = zero_mask & (1u << j);
-        Ln[0][j * 32 + lane] = z ? 0.0 : S.f[0][j];
-        Ln[1][j * 32 + lane] = z ? 0.0 : S.f[1][j];
-        Ln[2][j * 32 + lane] = S.f[2][j];
+        Ln[0][j * MAG_TEAM + tid] = z ? 0.0 : S.f[0][j];
+        Ln[1][j * MAG_TEAM + tid] = z ? 0.0 : S.f[1][j];
+        Ln[2][j * MAG_TEAM + tid] = S.f[2][j];
       }
       if (mir_mask & (1u << j)) {
         const int a = mir_addr[j];
@@ -331,62 +379,83 @@ __device__ __noinline__ bool run_timesteps_fast(Gal& G, RkShared* rs) {
       }
     }
   };
-  // unused slots of both lines must read as zero
-  for (int i = lane; i < 2 * 3 * MAG_FAST_MAXPPL * 32; i += 32) (&rs->line[0][0][0])[i] = 0.0;
-  __syncwarp();
+  // unused slots of both lines must read as (finite) zero
+  for (int i = tid; i < 2 * 3 * MAG_FAST_MAXPPL * MAG_TEAM; i += MAG_TEAM) (&rs->line[0][0][0])[i] = 0.0;
+  __syncthreads();
 
-  const double dt = G.dt;
   const double dg0 = dt * (8.0 / 15), dg1 = dt * (5.0 / 12), dg2 = dt * (3.0 / 4);
   const double dz0 = dt * (-17.0 / 60), dz1 = dt * (-5.0 / 12);
-  const double dtg = dt * G.a->U.t0_Gyr;
-  const int nsteps = G.nsteps;
-  double* ck[3] = {G.A(A_T0), G.A(A_T1), G.A(A_T2)};
+  const double dtg = C.dtg, t_Gyr = C.t_Gyr, tmk = C.tau_min_kappa;
+  // replicated scalar state (identical in all 64 threads)
+  double t = C.t, t_last = C.t_last_sign_choice;
+  int sign_nx = C.sign_nx;
+  bool refresh = C.refresh_sign != 0;
+  long long stages = 0;
+  double* ck[3] = {WA(A_T0), WA(A_T1), WA(A_T2)};
   int buf = 0;
   int jt = 1;
+  bool ok = true;
   while (jt <= nsteps) {
     const int nb = min(MAG_FAST_BLK, nsteps - jt + 1);
     // ---- checkpoint
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
-      const int g = lane * PPL + j;
+      const int g = tid * PPL + j;
       if (g < nx) { ck[0][g] = S.f[0][j]; ck[1][g] = S.f[1][j]; ck[2][g] = S.f[2][j]; }
     }
-    const double ck_t = G.t, ck_tl = G.t_last_sign_choice;
-    const bool ck_refresh = G.refresh_sign;
-    const int ck_sign_nx = G.sign_nx;
+    const double ck_t = t, ck_tl = t_last;
+    const bool ck_refresh = refresh;
+    const int ck_sign_nx = sign_nx;
     static_assert(sizeof(RngState) == 17 * sizeof(uint64_t), "RngState layout");
-    if (lane < 17) ((uint64_t*)&rs->rng_ck)[lane] = ((const uint64_t*)&rs->rng)[lane];
+    if (tid < 17) ((uint64_t*)&rs->rng_ck)[tid] = ((const uint64_t*)&rs->rng)[tid];
+    if (tid < 8) rs->red[tid] = 0u;
     bool signs_saved = false;
-    unsigned mB = 0, mA = 0;
+    // running maxima start from the block's initial state
+    unsigned mB = 0, mA = 0, nB = 0, nA = 0;
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+      const unsigned h0 = (unsigned)__double2hiint(S.f[0][j]) & 0x7fffffffu, h1 = (unsigned)__double2hiint(S.f[1][j]) & 0x7fffffffu;
+      const unsigned h2 = (unsigned)__double2hiint(S.f[2][j]) & 0x7fffffffu;
+      mB = max(mB, max(h0, h1)); mA = max(mA, h2);
+      if (mir_mask & (1u << j)) nB = max(nB, max(h0, h1));
+      if (near_mask & (1u << j)) nA = max(nA, h2);
+    }
     publish(buf);
     for (int s = 0; s < nb; s++) {
-      const double this_t = G.t_Gyr + dtg * (double)(jt + s);
+      const double this_t = t_Gyr + dtg * (double)(jt + s);
       // same order of RNG draws as the reference: update_floor_sign (dynamo.f90:196-198) may
       // draw Bfloor_sign, then the first pde of the step redraws the layer signs if flagged
       // or if the grid size changed (floor_field.f90:55-79)
-      update_floor_sign(G, this_t);
-      if (G.refresh_sign || G.sign_nx != nx) {
-        if (!signs_saved) {  // first refresh of the block: keep the old signs for a replay
-          const double* sg = G.A(A_SIGN); double* bk = G.A(A_OMK);
-          const int nsave = max(nx, ck_sign_nx);
-          for (int i = lane; i < nsave; i += 32) bk[i] = sg[i];
-          signs_saved = true;
-          __syncwarp();
+      const bool due = this_t - t_last > tmk;
+      if (due || refresh || sign_nx != nx) {
+        __syncthreads();
+        if (leader) {
+          if (!signs_saved) {  // first refresh of the block: keep the old signs for a replay
+            const double* sg = WA(A_SIGN); double* bk = WA(A_OMK);
+            const int nsave = max(nx, ck_sign_nx);
+            for (int i = tid; i < nsave; i += 32) bk[i] = sg[i];
+            __syncwarp();
+          }
+          if (due) (void)random_sign(*G);
+          refresh_signs(*G);
         }
-        refresh_signs(G);
+        signs_saved = true;
+        if (due) t_last = this_t;
+        refresh = false; sign_nx = nx;
+        __syncthreads();
         load_signed_floor();
       }
-      const bool last = (jt + s == nsteps);
-      fast_stage<PPL, COEF_REGS, 0>(S, G, rs->line, buf, dg0, dz0, Rk, pub_mask, zero_mask, mir_mask, mir_addr, reload, mB, mA, false);
+      double* alp_out = (jt + s == nsteps) ? WA(A_ALP) : nullptr;
+      fast_stage<PPL, W_SMEM, 0>(S, rs, tid, buf, dg0, dz0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr);
       buf ^= 1;
-      fast_stage<PPL, COEF_REGS, 1>(S, G, rs->line, buf, dg1, dz1, Rk, pub_mask, zero_mask, mir_mask, mir_addr, reload, mB, mA, false);
+      fast_stage<PPL, W_SMEM, 1>(S, rs, tid, buf, dg1, dz1, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr);
       buf ^= 1;
-      fast_stage<PPL, COEF_REGS, 2>(S, G, rs->line, buf, dg2, 0.0, Rk, pub_mask, zero_mask, mir_mask, mir_addr, reload, mB, mA, last);
+      fast_stage<PPL, W_SMEM, 2>(S, rs, tid, buf, dg2, 0.0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, alp_out);
       buf ^= 1;
       // t = t + dt*gam1 ; ttmp = t + dt*zet1 ; t = ttmp + dt*gam2 ; ttmp = t + dt*zet2 ; t = ttmp + dt*gam3
-      double tt = G.t + dg0;
+      double tt = t + dg0;
       tt = tt + dz0; tt = tt + dg1; tt = tt + dz1; tt = tt + dg2;
-      G.t = tt;
+      t = tt;
     }
     // ---- accept or replay the block
 #pragma unroll
@@ -394,48 +463,105 @@ __device__ __noinline__ bool run_timesteps_fast(Gal& G, RkShared* rs) {
       mB = max(mB, __shfl_xor_sync(FULL, mB, o));
       mA = max(mA, __shfl_xor_sync(FULL, mA, o));
     }
-    const double MB = __hiloint2double((int)mB + 1, 0), MA = __hiloint2double((int)mA + 1, 0);
-    if (mB < 0x7fe00000u && mA < 0x7fe00000u && guard_ok(gk, dt, MB, MA)) {
-      G.point_stages += (long long)nb * 3 * nx;
+    if ((tid & 31) == 0) { atomicMax(&rs->red[0], mB); atomicMax(&rs->red[1], mA); }
+    if (side >= 0) { atomicMax(&rs->red[2 + 2 * side], nB); atomicMax(&rs->red[3 + 2 * side], nA); }
+    __syncthreads();
+    const unsigned rB = rs->red[0], rA = rs->red[1];
+    bool accept = rB < 0x7fe00000u && rA < 0x7fe00000u;
+    if (accept) {
+      const double MB = __hiloint2double((int)rB + 1, 0), MA = __hiloint2double((int)rA + 1, 0);
+      accept = MB < 1e8 && MA < 1000.0;
+      for (int sd = 0; sd < 2 && accept; sd++) {
+        const double MBn = __hiloint2double((int)rs->red[2 + 2 * sd] + 1, 0), MAn = __hiloint2double((int)rs->red[3 + 2 * sd] + 1, 0);
+        accept = guard_side_ok(rs->gk[sd], dt, MBn, MAn);
+      }
+    }
+    __syncthreads();   // everyone has read rs->red before the next block clears it
+    if (accept) {
+      stages += (long long)nb * 3 * nx;
       jt += nb;
       continue;
     }
-    // replay with the generic path from the checkpoint
-    if (G.a->replays && lane == 0) atomicAdd(G.a->replays, 1);
-    for (int v = 0; v < 3; v++) {
-      double* f = G.A(A_F0 + v);
-      for (int i = lane; i < nx; i += 32) f[i] = ck[v][i];
+    // replay with the generic path from the checkpoint (leader warp), helper waits
+    if (leader) {
+      Gal& g = *G;
+      if (g.a->replays && tid == 0) atomicAdd(g.a->replays, 1);
+      for (int v = 0; v < 3; v++) {
+        double* f = WA(A_F0 + v);
+        for (int i = tid; i < nx; i += 32) f[i] = ck[v][i];
+      }
+      if (signs_saved) {
+        double* sg = WA(A_SIGN); const double* bk = WA(A_OMK);
+        const int nsave = max(nx, ck_sign_nx);
+        for (int i = tid; i < nsave; i += 32) sg[i] = bk[i];
+      }
+      if (tid < 17) ((uint64_t*)&rs->rng)[tid] = ((const uint64_t*)&rs->rng_ck)[tid];
+      g.t = ck_t; g.t_last_sign_choice = ck_tl; g.refresh_sign = ck_refresh; g.sign_nx = ck_sign_nx;
+      const long long ps0 = g.point_stages;
+      __syncwarp();
+      impose_bc(g, WA(A_F0), WA(A_F1), WA(A_F2));
+      const bool okg = run_steps_generic(g, jt, nb);
+      if (tid == 0) {
+        rs->call.ok = okg ? 1 : 0; rs->call.t = g.t; rs->call.t_last_sign_choice = g.t_last_sign_choice;
+        rs->call.refresh_sign = g.refresh_sign ? 1 : 0; rs->call.sign_nx = g.sign_nx;
+        rs->call.point_stages = g.point_stages - ps0;
+      }
+      g.point_stages = ps0;
     }
-    if (signs_saved) {
-      double* sg = G.A(A_SIGN); const double* bk = G.A(A_OMK);
-      const int nsave = max(nx, ck_sign_nx);
-      for (int i = lane; i < nsave; i += 32) sg[i] = bk[i];
-    }
-    if (lane < 17) ((uint64_t*)&rs->rng)[lane] = ((const uint64_t*)&rs->rng_ck)[lane];
-    G.t = ck_t; G.t_last_sign_choice = ck_tl; G.refresh_sign = ck_refresh; G.sign_nx = ck_sign_nx;
-    __syncwarp();
-    impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
-    if (!run_steps_generic(G, jt, nb)) return false;
+    __syncthreads();
+    ok = rs->call.ok != 0;
+    t = rs->call.t; t_last = rs->call.t_last_sign_choice; refresh = rs->call.refresh_sign != 0; sign_nx = rs->call.sign_nx;
+    stages += rs->call.point_stages;
+    __syncthreads();
+    if (!ok) break;
     jt += nb;
-    load_signed_floor();   // (a refresh still pending after the replay happens at the next step)
+    load_signed_floor();
     load_state();
   }
   // ---- hand the state back to the workspace (the caller applies impose_bc)
+  if (ok) {
 #pragma unroll
-  for (int j = 0; j < PPL; j++) {
-    const int g = lane * PPL + j;
-    if (g < nx) { G.A(A_F0)[g] = S.f[0][j]; G.A(A_F1)[g] = S.f[1][j]; G.A(A_F2)[g] = S.f[2][j]; }
+    for (int j = 0; j < PPL; j++) {
+      const int g = tid * PPL + j;
+      if (g < nx) { WA(A_F0)[g] = S.f[0][j]; WA(A_F1)[g] = S.f[1][j]; WA(A_F2)[g] = S.f[2][j]; }
+    }
   }
-  __syncwarp();
-  return true;
+  __syncthreads();
+  if (tid == 0) {
+    rs->call.ok = ok ? 1 : 0; rs->call.t = t; rs->call.t_last_sign_choice = t_last;
+    rs->call.refresh_sign = refresh ? 1 : 0; rs->call.sign_nx = sign_nx; rs->call.point_stages = stages;
+  }
+  __syncthreads();
 }
 
-// Returns ok (false: the field blew up, check_f_error).
-__device__ inline bool run_timesteps(Gal& G, RkShared* rs) {
+__device__ __forceinline__ void fast_dispatch(Gal* G, RkShared* rs) {
+  switch (rs->call.ppl) {
+    case 2: fast_loop_team<2, false>(G, rs); break;
+    case 3: fast_loop_team<3, true>(G, rs); break;
+    default: fast_loop_team<4, true>(G, rs); break;
+  }
+}
+
+// Leader warp: runs the time loop of the current snapshot attempt.  Returns ok (false: the
+// field blew up, check_f_error).
+__device__ bool run_timesteps(Gal& G, RkShared* rs) {
   if (G.nsteps < 1) return true;
-  if (G.a->use_fast) {
-    if (G.nx <= 128) return run_timesteps_fast<4, true>(G, rs);
-    if (G.nx <= 256) return run_timesteps_fast<8, false>(G, rs);
+  if (G.a->use_fast && G.nx >= 32 && G.nx <= MAG_FAST_MAXPPL * MAG_TEAM) {
+    if (G.lane == 0) {
+      FastCall& C = rs->call;
+      C.W = G.W; C.nxcap = G.a->nxcap; C.nx = G.nx; C.nsteps = G.nsteps;
+      C.ppl = G.nx <= 2 * MAG_TEAM ? 2 : (G.nx <= 3 * MAG_TEAM ? 3 : 4);
+      C.sign_nx = G.sign_nx; C.refresh_sign = G.refresh_sign ? 1 : 0; C.cmd = TEAM_CMD_FAST; C.ok = 1;
+      C.dt = G.dt; C.t = G.t; C.t_Gyr = G.t_Gyr; C.dtg = G.dt * G.a->U.t0_Gyr;
+      C.tau_min_kappa = G.a->P.p_floor_kappa * G.tau_min; C.t_last_sign_choice = G.t_last_sign_choice;
+      C.Rk = G.a->P.R_kappa; C.point_stages = 0;
+    }
+    __syncthreads();   // releases the helper warp (k_evolve)
+    fast_dispatch(&G, rs);
+    const FastCall& C = rs->call;
+    G.t = C.t; G.t_last_sign_choice = C.t_last_sign_choice; G.refresh_sign = C.refresh_sign != 0; G.sign_nx = C.sign_nx;
+    G.point_stages += C.point_stages;
+    return C.ok != 0;
   }
   return run_steps_generic(G, 1, G.nsteps);
 }

@@ -13,11 +13,15 @@
 #include <vector>
 
 #include "mag_galaxy.cuh"
+#include "mag_phases.cuh"
 #include "mag_rk_fast.cuh"
 
 using namespace magdev;
 
 #define WARPS_PER_CTA 4
+#ifndef MAG_EVOLVE_MAXREG
+#define MAG_EVOLVE_MAXREG 168   // 6 teams of 64 threads per SM
+#endif
 
 static thread_local std::string g_last_error;
 static void set_error(const std::string& s) { g_last_error = s; }
@@ -30,169 +34,98 @@ static void set_error(const std::string& s) { g_last_error = s; }
     }                                                                                          \
   } while (0)
 
-// ------------------------------------------------------------------ dynamo_run on a warp
-// dynamo.f90:39-300.  Returns true when the reference would return error=.true.
-__device__ static bool run_galaxy(Gal& G, RkShared* rs) {
-  const mag_params_t& P = G.a->P;
-  const bool test_run = P.p_no_magnetic_fields_test_run != 0;
-  const int lane = G.lane;
-  bool elliptical = false, ok = true;
-  if (lane == 0) rng_seed(G.rng, G.a->gal_ids[G.g], P.p_random_seed, P.rng_kind);
-  __syncwarp();
-  // initialize_floor_sign (floor_field.f90:116-123)
-  G.t_last_sign_choice = 0.0;
-  (void)random_sign(G);
-  G.refresh_sign = true;
-  G.sign_nx = -1;
-  G.status = test_run ? 't' : 'M';
-  G.flags = 0; G.point_stages = 0;
-  G.last_output = false;
-  G.t = 0; G.dt = 0; G.nsteps = 20; G.time_between_inputs = 0; G.minh = 1e10; G.maxetat = 0; G.tau_min = 0;
-  reset_outputs(G);
-  load_input_parameters(G);
-  if (set_input_params(G)) return true;
-  construct_grid(G);
-  {
-    const int ids[] = {A_F0, A_F1, A_F2, A_ALP, A_BZ, A_BEQ, A_TAU, A_LKPC, A_L, A_N, A_H, A_ETAT, A_ALPK};
-    for (int k = 0; k < (int)(sizeof(ids) / sizeof(int)); k++) {
-      double* p = G.A(ids[k]);
-      for (int i = lane; i < G.nx; i += 32) p[i] = 0.0;
-    }
-    __syncwarp();
-  }
-  bool able = construct_profiles(G);
-  int it = G.init_it;
-  if (!able) {  // finish()
-    estimate_Bzmod(G);
-    make_ts_arrays(G, it);
-    return false;
-  }
-  if (G.Mgas_disk < P.Mgas_disk_min) G.flags |= MAG_FLAG_STALE_PROFILES;
-  if (G.r_disk > P.p_rdisk_min && G.Mgas_disk > P.Mgas_disk_min) {
-    init_seed_field(G);
-    estimate_Bzmod(G);
-    impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
-  }
-  bool finish_needed = false;
-  for (it = G.init_it; it <= G.max_it; it++) {
-    if (G.r_disk < P.p_rdisk_min || G.Mgas_disk < P.Mgas_disk_min) {
-      elliptical = true;
-      for (int v = 0; v < 3; v++) { double* f = G.A(A_F0 + v); for (int i = lane; i < G.nx; i += 32) f[i] = 0.0; }
-      __syncwarp();
-    } else {
-      if (elliptical) {
-        able = construct_profiles(G);
-        init_seed_field(G);
-        estimate_Bzmod(G);
-        impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
-      }
-      if (able) elliptical = false;
-    }
-    if (it != G.init_it && !elliptical) {
-      if (!adjust_grid(G)) { if (lane == 0) atomicExch(G.a->fail, MAG_ERR_NX_OVERFLOW); return true; }
-      impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
-      able = construct_profiles(G);
-      if (!able) { G.last_output = true; finish_needed = true; break; }
-    }
-    set_timestep(G, true);
-    {  // f_snapshot_beginning = f
-      for (int v = 0; v < 3; v++) {
-        const double* f = G.A(A_F0 + v); double* fb = G.A(A_FB0 + v);
-        for (int i = lane; i < G.nx; i += 32) fb[i] = f[i];
-      }
-      __syncwarp();
-    }
-    for (int fail_count = 0; fail_count <= P.p_MAX_FAILS; fail_count++) {
-      ok = true;
-      if (test_run || elliptical) {
-        double *alp = G.A(A_ALP), *bz = G.A(A_BZ);
-        for (int i = lane; i < G.nx; i += 32) { alp[i] = 0.0; bz[i] = 0.0; }
-        __syncwarp();
-        break;
-      }
-      ok = run_timesteps(G, rs);
-      if (ok) break;
-      G.status = 'm';
-      G.flags |= MAG_FLAG_RETRY;
-      set_timestep(G, false);
-      for (int v = 0; v < 3; v++) {
-        double* f = G.A(A_F0 + v); const double* fb = G.A(A_FB0 + v);
-        for (int i = lane; i < G.nx; i += 32) f[i] = fb[i];
-      }
-      __syncwarp();
-    }
-    if (!ok) {
-      G.status = 'i';
-      G.last_output = true;
-      init_seed_field(G);
-    }
-    impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
-    estimate_Bzmod(G);
-    make_ts_arrays(G, it);
-    if (G.last_output) break;
-    G.status = test_run ? 't' : 'M';
-    if (set_input_params(G)) break;
-  }
-  if (finish_needed) {  // finish() is the only writer of this snapshot
-    estimate_Bzmod(G);
-    make_ts_arrays(G, it);
-  }
-  return false;
-}
-
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_dynamo_run(KernelArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// ------------------------------------------------------------------ Phase A kernel
+// One warp per galaxy, persistent, any order (every history costs about the same here).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_profiles(KernelArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * WARPS_PER_CTA + wib;
-  RkShared* rs = reinterpret_cast<RkShared*>(smem_raw) + wib;
   Gal G;
   G.a = &a;
   G.W = a.ws + (size_t)gw * A_COUNT * a.nxcap;
-  G.rng = &rs->rng;
+  G.rng = nullptr;
   G.lane = lane;
   for (;;) {
     int q = 0;
     if (lane == 0) q = atomicAdd(a.counter, 1);
     q = __shfl_sync(FULL, q, 0);
-    if (q >= a.ngal) break;
-    G.g = a.order ? a.order[q] : q;
-    const bool err = run_galaxy(G, rs);
+    if (q >= a.g1 - a.g0) break;
+    G.g = a.g0 + q;
+    GalHead H;
+    const bool err = run_profiles(G, H);
+    H.error = err ? 1 : 0;
+    if (err) H.cost = 0;
     if (lane == 0) {
-      if (a.out.error) a.out.error[G.g] = err ? 1 : 0;
-      if (a.out.nsteps) a.out.nsteps[G.g] = G.nsteps;
-      if (a.out.point_stages) a.out.point_stages[G.g] = G.point_stages;
-      if (a.out.flags) a.out.flags[G.g] = G.flags;
+      a.heads[q] = H;
+      if (a.out.error) a.out.error[G.g] = H.error;
+      if (err) {  // nothing else is written for this galaxy (dynamo.f90:69-73)
+        if (a.out.nsteps) a.out.nsteps[G.g] = G.nsteps;
+        if (a.out.point_stages) a.out.point_stages[G.g] = 0;
+        if (a.out.flags) a.out.flags[G.g] = G.flags;
+      }
     }
     __syncwarp();
   }
 }
 
-// ------------------------------------------------------------------ cost-ordered queue
-// Longest histories first (number of valid snapshots), so that the persistent warps do not
-// end on a 40-snapshot galaxy: a counting sort on the device.
-__global__ void k_cost_hist(const double* inputs, int ngal, int nz, double rdisk_min, int* key, int* hist) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ngal) return;
-  int init_it = -1, max_it = nz;
-  for (int i = 1; i <= nz; i++) {
-    double rd = inputs[(size_t)g * nz + i - 1];
-    if (rd >= rdisk_min && init_it < 0) init_it = i;
-    if (rd < 0 && init_it > 0) { max_it = i - 1; break; }
+// ------------------------------------------------------------------ Phase B kernel
+// One 64-thread team per galaxy, persistent, longest history first.  Warp 0 leads (seeds,
+// grid transformations of f, outputs, generic path); warp 1 joins for the fast time loop.
+__global__ void __maxnreg__(MAG_EVOLVE_MAXREG) k_evolve(KernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RkShared* rs = reinterpret_cast<RkShared*>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32) {  // helper warp
+    for (;;) {
+      __syncthreads();
+      if (rs->call.cmd == TEAM_CMD_EXIT) break;
+      fast_dispatch(nullptr, rs);
+    }
+    return;
   }
-  int k = init_it < 0 ? 0 : max_it - init_it + 1;
-  key[g] = k;
-  atomicAdd(&hist[k], 1);
+  Gal G;
+  G.a = &a;
+  G.W = a.ws2 + (size_t)blockIdx.x * A_COUNT * a.nxcap;
+  G.rng = &rs->rng;
+  G.lane = lane;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(a.counter2, 1);
+    q = __shfl_sync(FULL, q, 0);
+    if (q >= a.g1 - a.g0) break;
+    const int qi = a.order[q];
+    const GalHead H = a.heads[qi];
+    if (H.error) continue;
+    G.g = a.g0 + qi;
+    run_evolve(G, H, rs);
+  }
+  if (lane == 0) rs->call.cmd = TEAM_CMD_EXIT;
+  __syncthreads();
 }
-__global__ void k_cost_scan(int* hist, int nz) {  // descending exclusive scan, in place
+
+// ------------------------------------------------------------------ cost-ordered queue
+// Longest histories first (exact cost = sum of nsteps*nx known after Phase A): a counting
+// sort on 1/16-octave buckets of the cost.
+#define COST_BUCKETS 1024
+__device__ __forceinline__ int cost_bucket(long long c) {
+  if (c <= 0) return 0;
+  const int b = (int)(log2f((float)c) * 16.0f) + 1;
+  return b >= COST_BUCKETS ? COST_BUCKETS - 1 : b;
+}
+__global__ void k_cost_hist(const GalHead* heads, int n, int* hist) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomicAdd(&hist[cost_bucket(heads[i].cost)], 1);
+}
+__global__ void k_cost_scan(int* hist) {  // descending exclusive scan, in place
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
-    for (int k = nz; k >= 0; k--) { int c = hist[k]; hist[k] = acc; acc += c; }
+    for (int k = COST_BUCKETS - 1; k >= 0; k--) { int c = hist[k]; hist[k] = acc; acc += c; }
   }
 }
-__global__ void k_cost_scatter(const int* key, int ngal, int* hist, int* order) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ngal) return;
-  order[atomicAdd(&hist[key[g]], 1)] = g;
+__global__ void k_cost_scatter(const GalHead* heads, int n, int* hist, int* order) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  order[atomicAdd(&hist[cost_bucket(heads[i].cost)], 1)] = i;
 }
 
 // FP64 peak micro-benchmark: independent DFMA chains, 2 flops each
@@ -211,22 +144,29 @@ struct mag_ctx {
   mag_params_t P;
   int device = 0;
   int sm_count = 0;
-  int ctas_per_sm = 0;
-  int nwarps = 0;
+  int ctasA_per_sm = 0, ctasB_per_sm = 0;
+  int nwarpsA = 0, nteamsB = 0;
   int nxcap = 0;
-  double* ws = nullptr;
-  int* d_counter = nullptr;  // [0] queue head, [1] fail flag, [2] fast-path replays
+  double* wsA = nullptr;      // Phase A: per-warp workspaces
+  double* wsB = nullptr;      // Phase B: per-team workspaces
+  int* d_counter = nullptr;   // [0] A queue head, [1] fail flag, [2] fast-path replays, [3] B queue head
+  unsigned long long* d_arena_top = nullptr;
   int* d_hist = nullptr;
-  int* d_key = nullptr;
   int* d_order = nullptr;
-  int order_cap = 0;
+  SnapRec* d_recs = nullptr;
+  GalHead* d_heads = nullptr;
+  int chunk_cap = 0;          // galaxies the record tables are sized for
+  int nz_cap = 0;
+  double* d_arena = nullptr;
+  long long arena_cap = 0;    // doubles
   // staging for the host-buffer API
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double last_ms[4] = {0, 0, 0, 0};
   int last_launches = 0;
+  int last_replays = 0;
   int use_fast = 1;
 };
 
@@ -289,24 +229,32 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   c->sm_count = prop.multiProcessorCount;
   const char* env_fast = getenv("MAG_DISABLE_FAST_PATH");
   c->use_fast = (env_fast && env_fast[0] == '1') ? 0 : 1;
-  const size_t smem = sizeof(RkShared) * WARPS_PER_CTA;
-  CUDA_TRY(cudaFuncSetAttribute(k_dynamo_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dynamo_run, WARPS_PER_CTA * 32, smem));
-  if (occ < 1) { set_error("kernel does not fit on an SM"); delete c; return MAG_ERR_CUDA; }
-  c->ctas_per_sm = occ;
-  c->nwarps = c->sm_count * occ * WARPS_PER_CTA;
+  const size_t smemB = sizeof(RkShared);
+  CUDA_TRY(cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+  int occA = 0, occB = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, k_profiles, WARPS_PER_CTA * 32, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_evolve, MAG_TEAM, smemB));
+  if (occA < 1 || occB < 1) { set_error("kernel does not fit on an SM"); delete c; return MAG_ERR_CUDA; }
+  c->ctasA_per_sm = occA; c->ctasB_per_sm = occB;
+  c->nwarpsA = c->sm_count * occA * WARPS_PER_CTA;
+  c->nteamsB = c->sm_count * occB;
   const char* env_cap = getenv("MAG_NXCAP");
   int cap = env_cap ? atoi(env_cap) : 2048;
   if (cap > params->p_nx_MAX) cap = params->p_nx_MAX;
   if (cap < params->p_nx_ref + 6) cap = params->p_nx_ref + 6;
+  if (cap < MAG_FAST_MAXPPL * MAG_TEAM) cap = MAG_FAST_MAXPPL * MAG_TEAM;  // the fast path addresses up to 256 points
   c->nxcap = (cap + 15) & ~15;
-  CUDA_TRY(cudaMalloc(&c->ws, (size_t)c->nwarps * A_COUNT * c->nxcap * sizeof(double)));
-  CUDA_TRY(cudaMemset(c->ws, 0, (size_t)c->nwarps * A_COUNT * c->nxcap * sizeof(double)));
+  const size_t wsA = (size_t)c->nwarpsA * A_COUNT * c->nxcap * sizeof(double);
+  const size_t wsB = (size_t)c->nteamsB * A_COUNT * c->nxcap * sizeof(double);
+  CUDA_TRY(cudaMalloc(&c->wsA, wsA));
+  CUDA_TRY(cudaMemset(c->wsA, 0, wsA));
+  CUDA_TRY(cudaMalloc(&c->wsB, wsB));
+  CUDA_TRY(cudaMemset(c->wsB, 0, wsB));
   CUDA_TRY(cudaMalloc(&c->d_counter, 4 * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&c->d_hist, 4096 * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_arena_top, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&c->d_hist, COST_BUCKETS * sizeof(int)));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
   *ctx_out = c;
   return MAG_OK;
 }
@@ -314,9 +262,10 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
 void mag_destroy(mag_ctx_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->ws); cudaFree(c->d_counter); cudaFree(c->d_hist); cudaFree(c->d_key); cudaFree(c->d_order);
+  cudaFree(c->wsA); cudaFree(c->wsB); cudaFree(c->d_counter); cudaFree(c->d_arena_top); cudaFree(c->d_hist);
+  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena);
   cudaFree(c->d_stage);
-  for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -328,25 +277,46 @@ static int check_quantities(int32_t n_profile_q, const int32_t* profile_q, int32
   return MAG_OK;
 }
 
+// Record storage: SnapRec/GalHead tables for `chunk` galaxies and an arena for their arrays.
+// The arena budget per snapshot is R_COUNT arrays of ARENA_NX_BUDGET points (default grid
+// 107; grid extensions reach ~330 in the example input but are rare); a batch that does not
+// fit is solved in several chunks, and a chunk that overflows the arena is reported as
+// MAG_ERR_CUDA with an explanatory message.
+#define ARENA_NX_BUDGET 176
+static long long arena_need(int chunk, int nz) { return (long long)chunk * nz * R_COUNT * ARENA_NX_BUDGET; }
+
+static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
+  if (c->chunk_cap > 0 && nz <= c->nz_cap && (ngal <= c->chunk_cap)) { *chunk_out = ngal; return MAG_OK; }
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  free_b += (size_t)c->arena_cap * sizeof(double) + (size_t)c->chunk_cap * ((size_t)c->nz_cap * sizeof(SnapRec) + sizeof(GalHead) + sizeof(int));
+  const char* env = getenv("MAG_ARENA_FRACTION");
+  const double frac = env ? atof(env) : 0.5;
+  const size_t per_gal = (size_t)nz * sizeof(SnapRec) + sizeof(GalHead) + sizeof(int) + (size_t)arena_need(1, nz) * sizeof(double);
+  long long chunk = (long long)((double)free_b * frac / (double)per_gal);
+  if (chunk > ngal) chunk = ngal;
+  if (chunk < 1) { set_error("not enough device memory for the snapshot records"); return MAG_ERR_CUDA; }
+  if (chunk <= c->chunk_cap && nz <= c->nz_cap) { *chunk_out = (int)chunk; return MAG_OK; }
+  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena);
+  c->d_order = nullptr; c->d_recs = nullptr; c->d_heads = nullptr; c->d_arena = nullptr; c->chunk_cap = 0; c->arena_cap = 0;
+  CUDA_TRY(cudaMalloc(&c->d_order, (size_t)chunk * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_recs, (size_t)chunk * nz * sizeof(SnapRec)));
+  CUDA_TRY(cudaMalloc(&c->d_heads, (size_t)chunk * sizeof(GalHead)));
+  CUDA_TRY(cudaMalloc(&c->d_arena, (size_t)arena_need((int)chunk, nz) * sizeof(double)));
+  c->chunk_cap = (int)chunk; c->nz_cap = nz; c->arena_cap = arena_need((int)chunk, nz);
+  *chunk_out = (int)chunk;
+  return MAG_OK;
+}
+
 static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int32_t nz, const double* d_t,
                         const double* d_inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
                         const int32_t* scalar_q, const mag_outputs_t* d_out, cudaStream_t st) {
   if (nz < 1 || nz > 4000) { set_error("nz out of range"); return MAG_ERR_BAD_ARGUMENT; }
-  if (ngal > c->order_cap) {
-    cudaFree(c->d_key); cudaFree(c->d_order);
-    c->d_key = c->d_order = nullptr; c->order_cap = 0;
-    CUDA_TRY(cudaMalloc(&c->d_key, (size_t)ngal * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&c->d_order, (size_t)ngal * sizeof(int)));
-    c->order_cap = ngal;
-  }
+  int chunk = 0;
+  int rc = ensure_records(c, ngal, nz, &chunk);
+  if (rc) return rc;
   int launches = 0;
-  CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(int), st));
-  CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, (nz + 1) * sizeof(int), st));
-  const int tb = 256, gb = (ngal + tb - 1) / tb;
-  k_cost_hist<<<gb, tb, 0, st>>>(d_inputs /* column 0 = r_disk */, ngal, nz, c->P.p_rdisk_min, c->d_key, c->d_hist);
-  k_cost_scan<<<1, 32, 0, st>>>(c->d_hist, nz);
-  k_cost_scatter<<<gb, tb, 0, st>>>(c->d_key, ngal, c->d_hist, c->d_order);
-  launches += 3;
+  CUDA_TRY(cudaMemsetAsync(c->d_counter + 1, 0, 2 * sizeof(int), st));  // fail flag, replays
   KernelArgs a;
   memset(&a, 0, sizeof(a));
   a.P = c->P;
@@ -357,17 +327,33 @@ static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int3
   for (int i = 0; i < n_profile_q; i++) a.profile_q[i] = profile_q[i];
   for (int i = 0; i < n_scalar_q; i++) a.scalar_q[i] = scalar_q[i];
   a.out = *d_out;
-  a.ws = c->ws; a.nxcap = c->nxcap;
-  a.counter = c->d_counter; a.fail = c->d_counter + 1;
+  a.ws = c->wsA; a.ws2 = c->wsB; a.nxcap = c->nxcap;
+  a.counter = c->d_counter; a.fail = c->d_counter + 1; a.replays = c->d_counter + 2; a.counter2 = c->d_counter + 3;
   a.use_fast = c->use_fast;
-  a.replays = c->d_counter + 2;
-  int ctas = c->sm_count * c->ctas_per_sm;
-  const int need = (ngal + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  if (need < ctas) ctas = need;
-  const size_t smem = sizeof(RkShared) * WARPS_PER_CTA;
-  k_dynamo_run<<<ctas, WARPS_PER_CTA * 32, smem, st>>>(a);
-  launches += 1;
-  CUDA_TRY(cudaGetLastError());
+  a.recs = c->d_recs; a.heads = c->d_heads; a.arena = c->d_arena; a.arena_top = c->d_arena_top; a.arena_cap = c->arena_cap;
+  for (int g0 = 0; g0 < ngal; g0 += chunk) {
+    const int n = (ngal - g0 < chunk) ? ngal - g0 : chunk;
+    a.g0 = g0; a.g1 = g0 + n;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_counter + 3, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_arena_top, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, COST_BUCKETS * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_recs, 0, (size_t)n * nz * sizeof(SnapRec), st));
+    int ctasA = c->sm_count * c->ctasA_per_sm;
+    const int needA = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (needA < ctasA) ctasA = needA;
+    k_profiles<<<ctasA, WARPS_PER_CTA * 32, 0, st>>>(a);
+    const int tb = 256, gb = (n + tb - 1) / tb;
+    k_cost_hist<<<gb, tb, 0, st>>>(c->d_heads, n, c->d_hist);
+    k_cost_scan<<<1, 32, 0, st>>>(c->d_hist);
+    k_cost_scatter<<<gb, tb, 0, st>>>(c->d_heads, n, c->d_hist, c->d_order);
+    if (g0 == 0) CUDA_TRY(cudaEventRecord(c->ev[4], st));
+    int teams = c->nteamsB;
+    if (n < teams) teams = n;
+    k_evolve<<<teams, MAG_TEAM, sizeof(RkShared), st>>>(a);
+    launches += 5;
+    CUDA_TRY(cudaGetLastError());
+  }
   c->last_launches = launches;
   return MAG_OK;
 }
@@ -441,8 +427,9 @@ int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t 
   CUDA_TRY(cudaStreamSynchronize(st));
   float ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->last_ms[2] = ms;
-  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms; c->last_ms[0] = 0;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms;
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[3] = ms;
+  if (fail == MAG_ERR_ARENA) { set_error("snapshot-record arena exhausted (grids grew beyond the budget): lower MAG_ARENA_FRACTION chunking or split the batch"); return MAG_ERR_CUDA; }
   if (fail) { set_error("grid extension beyond p_nx_MAX / workspace capacity (reference: stop, grid.f90:222-226)"); return fail; }
   return MAG_OK;
 }
@@ -451,6 +438,7 @@ int mag_last_timing(mag_ctx_t* c, double ms_out[4]) {
   if (!c) return 0;
   float ms = 0;
   if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->last_ms[1] = ms;
+  if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[4]) == cudaSuccess) c->last_ms[0] = ms;  // profile phase (first chunk)
   for (int i = 0; i < 4; i++) ms_out[i] = c->last_ms[i];
   return c->last_launches;
 }
@@ -530,10 +518,11 @@ int mag_test_rng(int32_t igal, int32_t seed, int32_t kind, int32_t n, double* ou
 }
 int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nxcap, use_fast, replays of the last solve */) {
   if (!c) return MAG_ERR_BAD_ARGUMENT;
-  out[0] = c->sm_count; out[1] = c->ctas_per_sm; out[2] = c->nwarps; out[3] = c->nxcap; out[4] = c->use_fast;
+  out[0] = c->sm_count; out[1] = c->ctasA_per_sm; out[2] = c->nwarpsA; out[3] = c->nxcap; out[4] = c->use_fast;
   out[5] = 0;
   cudaSetDevice(c->device);
   cudaMemcpy(&out[5], c->d_counter + 2, sizeof(int), cudaMemcpyDeviceToHost);
+  out[6] = c->ctasA_per_sm; out[7] = c->ctasB_per_sm; out[8] = c->nteamsB;
   return MAG_OK;
 }
 int mag_set_fast_path(mag_ctx_t* c, int32_t on) {

@@ -20,7 +20,7 @@ from .abi import (ERROR_NAMES, MAG_NINPUT, MagOutputs, MagParams, PROFILE_ID, PR
                   SCALAR_NAMES)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmagnetizer_b200.so")
+LIB_PATH = os.environ.get("MAG_B200_LIB") or os.path.join(_HERE, "libmagnetizer_b200.so")
 _LIB = None
 
 
@@ -84,10 +84,10 @@ class DynamoSolver:
 
     # -- diagnostics ---------------------------------------------------------
     def info(self):
-        out = (C.c_int32 * 6)()
+        out = (C.c_int32 * 9)()
         _check(self._lib.mag_ctx_info(self._ctx, out), "mag_ctx_info")
-        return dict(sm_count=out[0], ctas_per_sm=out[1], nwarps=out[2], nxcap=out[3], use_fast=out[4],
-                    fast_path_replays=out[5])
+        return dict(sm_count=out[0], profile_ctas_per_sm=out[1], profile_warps=out[2], nxcap=out[3], use_fast=out[4],
+                    fast_path_replays=out[5], evolve_teams_per_sm=out[7], evolve_teams=out[8])
 
     def set_fast_path(self, on: bool):
         _check(self._lib.mag_set_fast_path(self._ctx, C.c_int32(1 if on else 0)), "mag_set_fast_path")
@@ -95,7 +95,7 @@ class DynamoSolver:
     def last_timing(self):
         ms = (C.c_double * 4)()
         n = self._lib.mag_last_timing(self._ctx, ms)
-        return dict(kernel_launches=n, ms_kernels=ms[1], ms_h2d=ms[2], ms_d2h=ms[3])
+        return dict(kernel_launches=n, ms_profile_phase=ms[0], ms_kernels=ms[1], ms_h2d=ms[2], ms_d2h=ms[3])
 
     def measure_fp64_peak(self, repeats=5) -> float:
         return float(self._lib.mag_measure_fp64_peak(self._ctx, repeats))
