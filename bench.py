@@ -184,7 +184,9 @@ def run_b200(args):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
     ms_dev = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    launches = solver.last_timing()["kernel_launches"]
+    tim_dev = solver.last_timing()
+    launches = tim_dev["kernel_launches"]
+    ms_evolve = tim_dev["ms_kernels"] - tim_dev["ms_profile_phase"]   # k_evolve of the last timed step
     W_rank = int(d_ps.sum().item())
     n_err = int(d_error.sum().item())
 
@@ -221,7 +223,7 @@ def run_b200(args):
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        flops = FLOP_PER_POINT_STAGE * W_rank / (ms_dev * 1e-3)
+        flops = FLOP_PER_POINT_STAGE * W_rank / (ms_evolve * 1e-3)
         alg_bytes = h2d + d2h
         # CPU baseline on rank 0: the oracle port on a bounded sample of the same workload
         cpu = None
@@ -253,12 +255,15 @@ def run_b200(args):
                        "point_stages_per_galaxy": W_all / G_all, "galaxies_with_error": n_err},
             "e2e": {"value": G_all / (ms_e2e_max * 1e-3), "unit": "galaxies/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e_max,
-                    "ms_h2d": tim["ms_h2d"], "ms_kernels": tim["ms_kernels"], "ms_d2h": tim["ms_d2h"]},
+                    "ms_h2d": tim["ms_h2d"], "ms_kernels": tim["ms_kernels"], "ms_profile_phase": tim["ms_profile_phase"],
+                    "ms_d2h": tim["ms_d2h"]},
             "gpu_launches": int(launches * args.steps),
             "roofline": {"bound": "fp64", "achieved": flops / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": flops / fp64_peak if fp64_peak else None, "traffic": None,
-                         "kernel": "k_dynamo_run", "flop_per_point_stage": FLOP_PER_POINT_STAGE,
-                         "point_stages_per_launch": W_rank,
+                         "kernel": "k_evolve", "flop_per_point_stage": FLOP_PER_POINT_STAGE,
+                         "point_stages_per_launch": W_rank, "kernel_ms": ms_evolve,
+                         "share_of_step": ms_evolve / ms_dev, "profile_phase_ms": tim_dev["ms_profile_phase"],
+                         "fast_path_replays": solver.info()["fast_path_replays"],
                          "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm": {"achieved": alg_bytes / (ms_dev * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / hbm_peak,

@@ -147,9 +147,8 @@ DET_FN void det_bessel_ik01(double x, double* i0, double* i1, double* k0, double
   if (x <= 8.0) {
     double t0 = 1.0, s0 = 1.0, t1 = 1.0, s1 = 1.0;
     for (int k = 1; k < 40; k++) {
-      const double dk = (double)k;
-      t0 *= q / (dk * dk);
-      t1 *= q / (dk * (dk + 1.0));
+      t0 *= q * DET_INV_KK[k];
+      t1 *= q * DET_INV_KK1[k];
       s0 += t0;
       s1 += t1;
       if (t0 < 1e-18 * s0) break;
@@ -167,13 +166,12 @@ DET_FN void det_bessel_ik01(double x, double* i0, double* i1, double* k0, double
     double t0 = 1.0, H = 0.0, s0 = 0.0;
     double t1 = 1.0, psi1 = -euler, psi2 = 1.0 - euler, s1 = (psi1 + psi2);
     for (int k = 1; k < 25; k++) {
-      const double dk = (double)k;
-      t0 *= q / (dk * dk);
-      H += 1.0 / dk;
+      t0 *= q * DET_INV_KK[k];
+      H += DET_INV_K[k];
       s0 += t0 * H;
-      t1 *= q / (dk * (dk + 1.0));
-      psi1 += 1.0 / dk;
-      psi2 += 1.0 / (dk + 1.0);
+      t1 *= q * DET_INV_KK1[k];
+      psi1 += DET_INV_K[k];
+      psi2 += DET_INV_K[k + 1];
       s1 += (psi1 + psi2) * t1;
     }
     *k0 = -(lg + euler) * (*i0) + s0;

@@ -247,9 +247,10 @@ __device__ __forceinline__ double halo_velocity(const RotCtx& c, double r) {
   const double B = (detmath::det_log(1.0 + cy) - cy / (1.0 + cy)) / y;
   return sqrt(fabs(c.halo_A * B));
 }
-__device__ inline double halo_velocity_contracted(const RotCtx& c, double r, bool at_centre, uint32_t* flags) {
-  // Vd2, Vb2 depend on r only (the reference recomputes them at every evaluation)
-  const double ob = bulge_omega(c, r), od = disk_omega(c, r);
+__device__ inline double halo_velocity_contracted(const RotCtx& c, double r, double od, double ob, bool at_centre, uint32_t* flags) {
+  // Vd2, Vb2 depend on |r| only: the reference recomputes disk_/bulge_rotation_curve at every
+  // residual evaluation (rotationCurves.f90:314-320); the values are bit-identical to the
+  // Omega_d, Omega_b of this radius (both use abs(r)), which the caller passes in
   const double Vb2 = (ob * r) * (ob * r), Vd2 = (od * r) * (od * r);
   auto fun = [&](double r0) {
     const double hv = halo_velocity(c, r0);
@@ -439,7 +440,7 @@ __device__ inline bool construct_profiles(Gal& G) {
     Om_d[i] = disk_omega(c, r);
     Om_b[i] = bulge_omega(c, r);
     double oh = 0.0;
-    if (with_halo) oh = halo_velocity_contracted(c, fabs(r), i == MAG_NGHOST, &fl) / r;
+    if (with_halo) oh = halo_velocity_contracted(c, fabs(r), Om_d[i], Om_b[i], i == MAG_NGHOST, &fl) / r;
     Om_h[i] = oh;
     Omk[i] = sqrt(Om_d[i] * Om_d[i] + Om_b[i] * Om_b[i] + oh * oh);
     const double d = fabs(r - rreg);

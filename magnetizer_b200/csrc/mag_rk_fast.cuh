@@ -35,7 +35,13 @@ namespace magdev {
 
 #define MAG_FAST_BLK 8        // steps per checkpoint block
 #define MAG_TEAM 64           // threads per galaxy team
-#define MAG_FAST_MAXPPL 4     // shared line sized for nx <= 256
+#define MAG_FAST_MAXPPL 8     // fast path up to nx = 512
+#define MAG_LINE_S (4 * MAG_TEAM + 8)   // shared line of the PPL <= 4 variants
+#define MAG_LINE_L (8 * MAG_TEAM + 8)   // shared line of the PPL = 8 variant
+// coefficient placement of a fast-loop variant
+#define COEF_REGS 0    // everything in registers (PPL = 2)
+#define COEF_WSMEM 1   // 7+1 stencil weights in shared memory, the rest in registers (PPL = 3, 4)
+#define COEF_GLOBAL 2  // everything re-read from the team workspace (L1/L2) every stage (PPL = 8)
 
 // parameters of one fast-loop call, written by the leader warp, read by both
 struct FastCall {
@@ -59,9 +65,13 @@ struct RkShared {
   FastCall call;
   GuardK gk[2];
   unsigned red[8];                                        // block maxima (high words)
-  double line[2][3][MAG_FAST_MAXPPL * MAG_TEAM];          // [buffer][variable][slot*64 + thread]
-  double wts[8][MAG_FAST_MAXPPL * MAG_TEAM];              // stencil weights for PPL >= 3
+  // lines: [buffer][variable][4 + global point index] with row length MAG_LINE_S or MAG_LINE_L
+  // (4 pad points each side, so that a thread's window -- own points +-3 -- is covered by
+  // 16-byte aligned vector loads); for COEF_WSMEM the stencil weights [k][slot*64 + thread]
+  // follow the short lines
+  alignas(16) double pool[2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM];
 };
+static_assert(2 * 3 * MAG_LINE_L <= 2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM, "RkShared pool too small for the long lines");
 
 // update_floor_sign (floor_field.f90:99-114)
 __device__ __forceinline__ void update_floor_sign(Gal& G, double time) {
@@ -186,43 +196,44 @@ __device__ __forceinline__ double fast_sqrt_abs(double x) {
   return fma(e, h, g);
 }
 
-template <int PPL, bool W_SMEM>
+template <int PPL, int MODE>
 struct FastState {
   double f[3][PPL], ft[3][PPL];
-  double w[W_SMEM ? 1 : PPL][7], w0a[W_SMEM ? 1 : PPL];
-  double ca[PPL], gs[PPL], fb[PPL], kdc[PPL], p3[PPL], qc[PPL], ak[PPL];
+  double w[MODE == COEF_REGS ? PPL : 1][7], w0a[MODE == COEF_REGS ? PPL : 1];
+  double ca[MODE == COEF_GLOBAL ? 1 : PPL], gs[MODE == COEF_GLOBAL ? 1 : PPL], fb[MODE == COEF_GLOBAL ? 1 : PPL];
+  double kdc[MODE == COEF_GLOBAL ? 1 : PPL], p3[MODE == COEF_GLOBAL ? 1 : PPL], qc[MODE == COEF_GLOBAL ? 1 : PPL];
+  double ak[MODE == COEF_GLOBAL ? 1 : PPL];
 };
-
-// address (slot*64 + thread) of the halo point at distance d (-3..-1, PPL..PPL+2) from this
-// thread's first point
-template <int PPL>
-__device__ __forceinline__ int halo_addr(int tid, int d) {
-  const int dthr = (d >= 0) ? d / PPL : -((-d + PPL - 1) / PPL);
-  const int slot = d - dthr * PPL;
-  return slot * MAG_TEAM + ((tid + dthr) & (MAG_TEAM - 1));
-}
+template <int PPL> struct LineLen { static constexpr int value = PPL <= 4 ? MAG_LINE_S : MAG_LINE_L; };
 
 // One Runge-Kutta stage.  STAGE: 0,1,2.  Reads the halo from line `buf`, updates f/ft in
 // registers, publishes the new state (boundary conditions applied) to the other line.
-template <int PPL, bool W_SMEM, int STAGE>
-__device__ __forceinline__ void fast_stage(FastState<PPL, W_SMEM>& S, RkShared* rs, int tid, int buf, double dg, double dz,
+template <int PPL, int MODE, int STAGE>
+__device__ __forceinline__ void fast_stage(FastState<PPL, MODE>& S, RkShared* rs, int tid, int buf, double dg, double dz,
                                            double Rk, uint32_t pub_mask, uint32_t zero_mask, uint32_t mir_mask,
                                            uint32_t near_mask, const int* mir_addr, bool reload, unsigned& mB, unsigned& mA,
-                                           unsigned& nB, unsigned& nA, double* alp_out) {
+                                           unsigned& nB, unsigned& nA, double* alp_out, const double* W, int nxcap) {
+  constexpr int LL = LineLen<PPL>::value;
+  const double* wts = rs->pool + 2 * 3 * MAG_LINE_S;
   __syncthreads();
   // ---- gather the window: PPL own points + 3 halo points each side
   double win[3][PPL + 6];
+  const int g0 = tid * PPL;
 #pragma unroll
   for (int v = 0; v < 3; v++) {
-    const double* L = rs->line[buf][v];
+    const double* L = rs->pool + (buf * 3 + v) * LL + 4 + g0;   // L[d] = point g0 + d
+    if (PPL % 2 == 0) {  // g0 even: 16-byte aligned pairs (g0-4,g0-3) (g0-2,g0-1) | (g0+PPL,..) (g0+PPL+2,..)
+      const double2 a = *reinterpret_cast<const double2*>(L - 4), b = *reinterpret_cast<const double2*>(L - 2);
+      const double2 c = *reinterpret_cast<const double2*>(L + PPL), d = *reinterpret_cast<const double2*>(L + PPL + 2);
+      win[v][0] = a.y; win[v][1] = b.x; win[v][2] = b.y;
+      win[v][PPL + 3] = c.x; win[v][PPL + 4] = c.y; win[v][PPL + 5] = d.x;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      win[v][k] = L[halo_addr<PPL>(tid, k - 3)];
-      win[v][PPL + 3 + k] = L[halo_addr<PPL>(tid, PPL + k)];
+      for (int k = 0; k < 3; k++) { win[v][k] = L[k - 3]; win[v][PPL + 3 + k] = L[PPL + k]; }
     }
     if (reload) {  // threads that own ghost / Dirichlet points take the boundary-conditioned values
 #pragma unroll
-      for (int j = 0; j < PPL; j++) S.f[v][j] = L[j * MAG_TEAM + tid];
+      for (int j = 0; j < PPL; j++) S.f[v][j] = L[j];
     }
 #pragma unroll
     for (int j = 0; j < PPL; j++) win[v][3 + j] = S.f[v][j];
@@ -230,15 +241,32 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, W_SMEM>& S, RkShared* 
   // ---- RHS and update, point by point
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
-    double w[7], w0a;
-    if (W_SMEM) {
+    double w[7], w0a, c_ca, c_gs, c_fb, c_kdc, c_p3, c_qc, c_ak;
+    if (MODE == COEF_WSMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) w[k] = rs->wts[k][j * MAG_TEAM + tid];
-      w0a = rs->wts[7][j * MAG_TEAM + tid];
+      for (int k = 0; k < 7; k++) w[k] = wts[(k * 4 + j) * MAG_TEAM + tid];
+      w0a = wts[(7 * 4 + j) * MAG_TEAM + tid];
+    } else if (MODE == COEF_REGS) {
+#pragma unroll
+      for (int k = 0; k < 7; k++) w[k] = S.w[MODE == COEF_REGS ? j : 0][k];
+      w0a = S.w0a[MODE == COEF_REGS ? j : 0];
     } else {
+      const int g = g0 + j;
 #pragma unroll
-      for (int k = 0; k < 7; k++) w[k] = S.w[W_SMEM ? 0 : j][k];
-      w0a = S.w0a[W_SMEM ? 0 : j];
+      for (int k = 0; k < 7; k++) w[k] = W[(size_t)(C_W0 + k) * nxcap + g];
+      w0a = W[(size_t)C_W0A * nxcap + g];
+    }
+    if (MODE == COEF_GLOBAL) {
+      const int g = g0 + j;
+      c_ca = W[(size_t)F_CA * nxcap + g]; c_gs = W[(size_t)F_GS * nxcap + g]; c_fb = W[(size_t)C_FBS * nxcap + g];
+      c_kdc = W[(size_t)F_KDC * nxcap + g]; c_p3 = W[(size_t)F_P3 * nxcap + g]; c_qc = W[(size_t)F_QC * nxcap + g];
+      c_ak = W[(size_t)F_AK * nxcap + g];
+    } else {
+      constexpr int jj = 0;
+      (void)jj;
+      c_ca = S.ca[MODE == COEF_GLOBAL ? 0 : j]; c_gs = S.gs[MODE == COEF_GLOBAL ? 0 : j]; c_fb = S.fb[MODE == COEF_GLOBAL ? 0 : j];
+      c_kdc = S.kdc[MODE == COEF_GLOBAL ? 0 : j]; c_p3 = S.p3[MODE == COEF_GLOBAL ? 0 : j]; c_qc = S.qc[MODE == COEF_GLOBAL ? 0 : j];
+      c_ak = S.ak[MODE == COEF_GLOBAL ? 0 : j];
     }
     const double Br = win[0][3 + j], Bp = win[1][3 + j], am = win[2][3 + j];
     double LBr = w[0] * win[0][j], LBp = w[0] * win[1][j], Lam = w[0] * win[2][j];
@@ -248,13 +276,13 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, W_SMEM>& S, RkShared* 
       LBp = fma(w[k], win[1][j + k], LBp);
       if (k != 3) Lam = fma(w[k], win[2][j + k], Lam);
     }
-    const double a = S.ak[j] + am;
+    const double a = c_ak + am;
     if (alp_out) alp_out[tid * PPL + j] = a;
-    const double p0 = fma(-(S.ca[j] * a), Bp, LBr);
-    const double p1 = fma(S.fb[j], fma(S.kdc[j], a, 1.0), fma(S.gs[j], Br, LBp));
+    const double p0 = fma(-(c_ca * a), Bp, LBr);
+    const double p1 = fma(c_fb, fma(c_kdc, a, 1.0), fma(c_gs, Br, LBp));
     const double B2 = fma(Br, Br, Bp * Bp);
-    const double em = fma(S.qc[j] * fast_sqrt_abs(a) * Br, Bp, a * B2);
-    const double p2 = fma(S.p3[j], em, fma(Rk, Lam, w0a * am));
+    const double em = fma(c_qc * fast_sqrt_abs(a) * Br, Bp, a * B2);
+    const double p2 = fma(c_p3, em, fma(Rk, Lam, w0a * am));
     const double b0 = (STAGE == 0) ? Br : S.ft[0][j];
     const double b1 = (STAGE == 0) ? Bp : S.ft[1][j];
     const double b2 = (STAGE == 0) ? am : S.ft[2][j];
@@ -267,14 +295,23 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, W_SMEM>& S, RkShared* 
     mA = max(mA, (unsigned)__double2hiint(n2) & 0x7fffffffu);
   }
   // ---- publish the new state with boundary conditions applied
-  double (*Ln)[MAG_FAST_MAXPPL * MAG_TEAM] = rs->line[buf ^ 1];
+  double* Ln = rs->pool + (buf ^ 1) * 3 * LL;   // Ln[v*LL + 4 + g]
+  if (PPL % 2 == 0 && !reload) {  // plain interior thread: vector stores
 #pragma unroll
-  for (int j = 0; j < PPL; j++) {
-    if (pub_mask & (1u << j)) {
-      const bool z = zero_mask & (1u << j);
-      Ln[0][j * MAG_TEAM + tid] = z ? 0.0 : S.f[0][j];
-      Ln[1][j * MAG_TEAM + tid] = z ? 0.0 : S.f[1][j];
-      Ln[2][j * MAG_TEAM + tid] = S.f[2][j];
+    for (int j = 0; j < PPL; j += 2) {
+      *reinterpret_cast<double2*>(&Ln[4 + g0 + j]) = make_double2(S.f[0][j], S.f[0][j + 1]);
+      *reinterpret_cast<double2*>(&Ln[LL + 4 + g0 + j]) = make_double2(S.f[1][j], S.f[1][j + 1]);
+      *reinterpret_cast<double2*>(&Ln[2 * LL + 4 + g0 + j]) = make_double2(S.f[2][j], S.f[2][j + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+      if (pub_mask & (1u << j)) {
+        const bool z = zero_mask & (1u << j);
+        Ln[4 + g0 + j] = z ? 0.0 : S.f[0][j];
+        Ln[LL + 4 + g0 + j] = z ? 0.0 : S.f[1][j];
+        Ln[2 * LL + 4 + g0 + j] = S.f[2][j];
+      }
     }
   }
   if (near_mask) {  // the few threads next to a boundary
@@ -282,7 +319,7 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, W_SMEM>& S, RkShared* 
     for (int j = 0; j < PPL; j++) {
       if (mir_mask & (1u << j)) {
         const int a = mir_addr[j];
-        Ln[0][a] = -S.f[0][j]; Ln[1][a] = -S.f[1][j]; Ln[2][a] = S.f[2][j];
+        Ln[a] = -S.f[0][j]; Ln[LL + a] = -S.f[1][j]; Ln[2 * LL + a] = S.f[2][j];
         nB = max(nB, max((unsigned)__double2hiint(S.f[0][j]) & 0x7fffffffu, (unsigned)__double2hiint(S.f[1][j]) & 0x7fffffffu));
       }
       if (near_mask & (1u << j)) nA = max(nA, (unsigned)__double2hiint(S.f[2][j]) & 0x7fffffffu);
@@ -293,8 +330,10 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, W_SMEM>& S, RkShared* 
 // Fast time loop of one snapshot attempt, executed by all 64 threads of the team.  G is the
 // leader warp's galaxy state (nullptr in the helper warp).  The result is left in rs->call
 // (ok, t, t_last_sign_choice, sign_nx, refresh_sign, point_stages) and in the workspace.
-template <int PPL, bool W_SMEM>
+template <int PPL, int MODE>
 __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
+  constexpr int LL = LineLen<PPL>::value;
+  double* const wts = rs->pool + 2 * 3 * MAG_LINE_S;
   const int tid = threadIdx.x;
   const bool leader = tid < 32;
   const FastCall C = rs->call;
@@ -322,12 +361,12 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
     int dst = -1;
     if (g > MAG_NGHOST && g <= 2 * MAG_NGHOST) dst = 2 * MAG_NGHOST - g;          // 4,5,6 -> 2,1,0
     if (g < m && g >= m - MAG_NGHOST) dst = 2 * m - g;                            // m-1.. -> m+1..
-    if (dst >= 0) { mir_mask |= 1u << j; mir_addr[j] = (dst % PPL) * MAG_TEAM + dst / PPL; }
+    if (dst >= 0) { mir_mask |= 1u << j; mir_addr[j] = 4 + dst; }
     if (dst >= 0 || g == MAG_NGHOST || g == m) { near_mask |= 1u << j; side = (g <= 2 * MAG_NGHOST) ? 0 : 1; }
     if (ghost || g == MAG_NGHOST || g == m) reload = true;
   }
 
-  FastState<PPL, W_SMEM> S;
+  FastState<PPL, MODE> S;
   auto load_state = [&]() {
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
@@ -342,45 +381,50 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
       const int g = tid * PPL + j;
-      S.fb[j] = (g >= MAG_NGHOST && g <= m) ? sg[g] * cFB[g] : 0.0;
+      const double v = (g >= MAG_NGHOST && g <= m) ? sg[g] * cFB[g] : 0.0;
+      if (MODE == COEF_GLOBAL) WA(C_FBS)[g] = v; else S.fb[MODE == COEF_GLOBAL ? 0 : j] = v;
     }
   };
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
     const int g = tid * PPL + j;
-    if (W_SMEM) {
+    if (MODE == COEF_WSMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) rs->wts[k][j * MAG_TEAM + tid] = WA(C_W0 + k)[g];
-      rs->wts[7][j * MAG_TEAM + tid] = WA(C_W0A)[g];
-    } else {
+      for (int k = 0; k < 7; k++) wts[(k * 4 + j) * MAG_TEAM + tid] = WA(C_W0 + k)[g];
+      wts[(7 * 4 + j) * MAG_TEAM + tid] = WA(C_W0A)[g];
+    } else if (MODE == COEF_REGS) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) S.w[W_SMEM ? 0 : j][k] = WA(C_W0 + k)[g];
-      S.w0a[W_SMEM ? 0 : j] = WA(C_W0A)[g];
+      for (int k = 0; k < 7; k++) S.w[MODE == COEF_REGS ? j : 0][k] = WA(C_W0 + k)[g];
+      S.w0a[MODE == COEF_REGS ? j : 0] = WA(C_W0A)[g];
     }
-    S.ca[j] = WA(F_CA)[g]; S.gs[j] = WA(F_GS)[g]; S.kdc[j] = WA(F_KDC)[g];
-    S.p3[j] = WA(F_P3)[g]; S.qc[j] = WA(F_QC)[g]; S.ak[j] = WA(F_AK)[g];
+    if (MODE != COEF_GLOBAL) {
+      S.ca[MODE == COEF_GLOBAL ? 0 : j] = WA(F_CA)[g]; S.gs[MODE == COEF_GLOBAL ? 0 : j] = WA(F_GS)[g];
+      S.kdc[MODE == COEF_GLOBAL ? 0 : j] = WA(F_KDC)[g]; S.p3[MODE == COEF_GLOBAL ? 0 : j] = WA(F_P3)[g];
+      S.qc[MODE == COEF_GLOBAL ? 0 : j] = WA(F_QC)[g]; S.ak[MODE == COEF_GLOBAL ? 0 : j] = WA(F_AK)[g];
+    }
   }
   load_signed_floor();
   load_state();
 
   auto publish = [&](int buf) {
-    double (*Ln)[MAG_FAST_MAXPPL * MAG_TEAM] = rs->line[buf];
+    double* Ln = rs->pool + buf * 3 * LL;
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
       if (pub_mask & (1u << j)) {
         const bool z = zero_mask & (1u << j);
-        Ln[0][j * MAG_TEAM + tid] = z ? 0.0 : S.f[0][j];
-        Ln[1][j * MAG_TEAM + tid] = z ? 0.0 : S.f[1][j];
-        Ln[2][j * MAG_TEAM + tid] = S.f[2][j];
+        Ln[4 + tid * PPL + j] = z ? 0.0 : S.f[0][j];
+        Ln[LL + 4 + tid * PPL + j] = z ? 0.0 : S.f[1][j];
+        Ln[2 * LL + 4 + tid * PPL + j] = S.f[2][j];
       }
       if (mir_mask & (1u << j)) {
         const int a = mir_addr[j];
-        Ln[0][a] = -S.f[0][j]; Ln[1][a] = -S.f[1][j]; Ln[2][a] = S.f[2][j];
+        Ln[a] = -S.f[0][j]; Ln[LL + a] = -S.f[1][j]; Ln[2 * LL + a] = S.f[2][j];
       }
     }
   };
   // unused slots of both lines must read as (finite) zero
-  for (int i = tid; i < 2 * 3 * MAG_FAST_MAXPPL * MAG_TEAM; i += MAG_TEAM) (&rs->line[0][0][0])[i] = 0.0;
+  __syncthreads();   // (the weights above live behind the short lines; the long lines overlap them)
+  for (int i = tid; i < 2 * 3 * LL; i += MAG_TEAM) rs->pool[i] = 0.0;
   __syncthreads();
 
   const double dg0 = dt * (8.0 / 15), dg1 = dt * (5.0 / 12), dg2 = dt * (3.0 / 4);
@@ -446,11 +490,11 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
         load_signed_floor();
       }
       double* alp_out = (jt + s == nsteps) ? WA(A_ALP) : nullptr;
-      fast_stage<PPL, W_SMEM, 0>(S, rs, tid, buf, dg0, dz0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr);
+      fast_stage<PPL, MODE, 0>(S, rs, tid, buf, dg0, dz0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr, W, nxcap);
       buf ^= 1;
-      fast_stage<PPL, W_SMEM, 1>(S, rs, tid, buf, dg1, dz1, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr);
+      fast_stage<PPL, MODE, 1>(S, rs, tid, buf, dg1, dz1, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr, W, nxcap);
       buf ^= 1;
-      fast_stage<PPL, W_SMEM, 2>(S, rs, tid, buf, dg2, 0.0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, alp_out);
+      fast_stage<PPL, MODE, 2>(S, rs, tid, buf, dg2, 0.0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, alp_out, W, nxcap);
       buf ^= 1;
       // t = t + dt*gam1 ; ttmp = t + dt*zet1 ; t = ttmp + dt*gam2 ; ttmp = t + dt*zet2 ; t = ttmp + dt*gam3
       double tt = t + dg0;
@@ -536,9 +580,10 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
 
 __device__ __forceinline__ void fast_dispatch(Gal* G, RkShared* rs) {
   switch (rs->call.ppl) {
-    case 2: fast_loop_team<2, false>(G, rs); break;
-    case 3: fast_loop_team<3, true>(G, rs); break;
-    default: fast_loop_team<4, true>(G, rs); break;
+    case 2: fast_loop_team<2, COEF_REGS>(G, rs); break;
+    case 3: fast_loop_team<3, COEF_WSMEM>(G, rs); break;
+    case 4: fast_loop_team<4, COEF_WSMEM>(G, rs); break;
+    default: fast_loop_team<8, COEF_GLOBAL>(G, rs); break;
   }
 }
 
@@ -550,7 +595,7 @@ __device__ bool run_timesteps(Gal& G, RkShared* rs) {
     if (G.lane == 0) {
       FastCall& C = rs->call;
       C.W = G.W; C.nxcap = G.a->nxcap; C.nx = G.nx; C.nsteps = G.nsteps;
-      C.ppl = G.nx <= 2 * MAG_TEAM ? 2 : (G.nx <= 3 * MAG_TEAM ? 3 : 4);
+      C.ppl = G.nx <= 2 * MAG_TEAM ? 2 : (G.nx <= 3 * MAG_TEAM ? 3 : (G.nx <= 4 * MAG_TEAM ? 4 : 8));
       C.sign_nx = G.sign_nx; C.refresh_sign = G.refresh_sign ? 1 : 0; C.cmd = TEAM_CMD_FAST; C.ok = 1;
       C.dt = G.dt; C.t = G.t; C.t_Gyr = G.t_Gyr; C.dtg = G.dt * G.a->U.t0_Gyr;
       C.tau_min_kappa = G.a->P.p_floor_kappa * G.tau_min; C.t_last_sign_choice = G.t_last_sign_choice;

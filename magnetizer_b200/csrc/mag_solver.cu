@@ -19,6 +19,9 @@
 using namespace magdev;
 
 #define WARPS_PER_CTA 4
+#ifndef MAG_PROFILE_MAXREG
+#define MAG_PROFILE_MAXREG 128   // 16 warps per SM: the profile phase is latency bound (serial root-finder chains)
+#endif
 #ifndef MAG_EVOLVE_MAXREG
 #define MAG_EVOLVE_MAXREG 168   // 6 teams of 64 threads per SM
 #endif
@@ -36,7 +39,7 @@ static void set_error(const std::string& s) { g_last_error = s; }
 
 // ------------------------------------------------------------------ Phase A kernel
 // One warp per galaxy, persistent, any order (every history costs about the same here).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_profiles(KernelArgs a) {
+__global__ void __maxnreg__(MAG_PROFILE_MAXREG) k_profiles(KernelArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * WARPS_PER_CTA + wib;
   Gal G;

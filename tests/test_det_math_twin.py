@@ -29,4 +29,4 @@ def test_bessel_tables_are_identical():
         return re.findall(r"^\s+(-?[0-9][0-9.e+-]*)[,}]", open(path).read(), flags=re.M)
     a = lits(os.path.join(ROOT, "oracle", "bessel_coeffs.hpp"))
     b = lits(os.path.join(ROOT, "magnetizer_b200", "csrc", "mag_bessel_coeffs.cuh"))
-    assert len(a) == 28 + 28 + 29 + 29 and a == b
+    assert len(a) == 28 + 28 + 29 + 29 + 41 + 41 + 42 and a == b

@@ -17,6 +17,9 @@ if __name__ == "__main__":
     # a bounded kernel (~0.1-0.3 s) whatever n, so that ncu's ~40 replays stay short
     gid = int(sys.argv[2]) if len(sys.argv) > 2 else 24
     inputs = np.ascontiguousarray(np.repeat(base[:, gid - 1:gid, :], n, axis=1))
+    if len(sys.argv) > 3:  # truncate the history after this many valid snapshots
+        first = int(np.argmax(inputs[0, 0] >= 0.5))
+        inputs[0, :, first + int(sys.argv[3]):] = -1.0e10
     ids = np.full(n, gid, np.int32)
     s = DynamoSolver(device=0)
     prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax",)
