@@ -230,10 +230,28 @@ int mag_solve_batch_device(mag_ctx_t *ctx, int32_t ngal, const int32_t *d_gal_id
                            int32_t n_scalar_q, const int32_t *scalar_q,
                            const mag_outputs_t *d_out, void *cuda_stream);
 
+/*
+ * Multi-GPU form: replaces the MPI master/worker farm of jobs_distribute
+ * (source/distributor.f90:253-384) for this operator.  The catalogue is cut into chunks of
+ * `chunk` galaxies; GPU number d of `devices[ndev]` owns the chunks k with k % ndev == d
+ * (static share) and steals unclaimed chunks from the other GPUs' shares when its own is
+ * exhausted; one host thread per GPU drives mag_solve_batch and the results are gathered
+ * into `out` (HOST buffers, same layouts as mag_solve_batch) in galaxy order.  There is no
+ * collective: galaxies are independent.  chunks_done / chunks_stolen ([ndev], may be NULL)
+ * report how the work ended up distributed.  The same device may be listed more than once.
+ */
+int mag_solve_partitioned(const mag_params_t *params, int32_t ndev, const int32_t *devices,
+                          int32_t ngal, const int32_t *gal_ids, int32_t nz, const double *t_gyr,
+                          const double *inputs, int32_t n_profile_q, const int32_t *profile_q,
+                          int32_t n_scalar_q, const int32_t *scalar_q, const mag_outputs_t *out,
+                          int32_t chunk, int32_t *chunks_done, int32_t *chunks_stolen);
+const char *mag_partition_last_error(void);
+
 /* Per-phase device time (ms, CUDA events on the solve stream) of the last
  * mag_solve_batch/_device call on this context, after the stream is synchronised:
  * [0] grid + profile kernels, [1] evolve kernel, [2] H2D, [3] D2H.  Returns the
- * number of kernel launches of that call. */
+ * number of kernel launches of that call.  [0] = profile phase (k_profiles + queue sort),
+ * [1] = all kernels (profile phase + k_evolve). */
 int mag_last_timing(mag_ctx_t *ctx, double ms_out[4]);
 
 /* FP64 DFMA micro-benchmark on the context's device: returns achieved FLOP/s

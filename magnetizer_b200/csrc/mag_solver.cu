@@ -486,6 +486,21 @@ int mag_test_bessel(const double* x, int n, double* out /* [4][n] */) {
   cudaFree(dx); cudaFree(dout);
   return MAG_OK;
 }
+__global__ void k_test_fast_sqrt(int n, const double* x, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fast_sqrt_abs(x[i]);
+}
+// the hot loop's sqrt|x| (mag_rk_fast.cuh)
+int mag_test_fast_sqrt(int32_t n, const double* x, double* out) {
+  double *dx = nullptr, *dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dx, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&dout, sizeof(double) * n));
+  CUDA_TRY(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  k_test_fast_sqrt<<<(n + 127) / 128, 128>>>(n, dx, dout);
+  CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dout);
+  return MAG_OK;
+}
 __global__ void k_test_det(int which, int n, const double* x, const double* y, double* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -1,0 +1,235 @@
+// magnetizer_main.cpp -- C++ host driver of the B200 dynamo path.
+//
+// Mirrors the reference's main program for this operator:
+//   program magnetizer (source/Magnetizer.f90:18-38)
+//     jobs_prepare            -> read the parameter file (namelists) and the input file
+//     jobs_reads_galaxy_list  -> optional 1-based galaxy ids on the command line (single-galaxy mode)
+//     jobs_distribute(dynamo_run, write_output, ...)  (source/distributor.f90:180)
+//                             -> mag_solve_partitioned: static + work-stealing chunks over the GPUs
+//     write_output            -> unit conversion table of source/output.f90:63-201, Log/* datasets
+// The reference cannot be built in this image (no Fortran/MPI/HDF5/GSL toolchain), so the
+// host side above the C ABI is C++; INTEGRATION.md shows the ISO_C_BINDING shim that lets the
+// unchanged Fortran driver call the same entry points.
+//
+// Input: the reference's HDF5 input file (own minimal reader).  Output: the reference's
+// dataset names and shapes (Output/<q> [ngal][nx][nz], scalars [ngal][nz], Log/status ...),
+// stored as an uncompressed .npz container (readable with numpy.load); the native HDF5
+// writer is SURVEY.md row 8(f1), not part of this round.
+//
+//   Magnetizer_b200 <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.npz]
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <zlib.h>
+
+#include "../../include/magnetizer_b200.h"
+#include "mag_hdf5_reader.hpp"
+#include "mag_namelist.hpp"
+
+namespace {
+
+const char* const kProfileNames[MAG_NPROFILE] = {"Br", "Bp", "alp_m", "Bzmod", "h", "Omega", "Omega_b", "Omega_d", "Omega_h",
+                                                 "Shear", "l", "v", "etat", "tau", "alp_k", "alp", "Uz", "Ur", "n", "Beq", "rkpc"};
+const char* const kScalarNames[MAG_NSCALAR] = {"t_Gyr", "dt", "rmax", "Bmax", "Bmax_idx", "Bavg", "Beavg"};
+
+// write_output's unit factors (output.f90:63-201 with constants.f90:40-74)
+double unit_factor(const std::string& q) {
+  const double km_kpc = 3.08567758e16, mp_g = 1.67262158e-24;
+  const double t0_kpcskm = 1.0 / (1.0 / 3 * 0.1 * 10.0), t0_s = t0_kpcskm * km_kpc, h0_km = km_kpc, h0_cm = h0_km * 1e5;
+  const double vel = h0_km / t0_s, n0_cm3 = (1.0 / 1e6) * (1.0 / 1e6) / (h0_cm * h0_cm) * (t0_s * t0_s) / mp_g;
+  if (q == "alp_m" || q == "alp_k" || q == "alp" || q == "v" || q == "Uz" || q == "Omega" || q == "Shear" || q == "etat") return vel;
+  if (q == "h" || q == "l") return 1e3;
+  if (q == "n") return n0_cm3;
+  return 1.0;
+}
+
+// ---- uncompressed .npz (zip of .npy files, "stored" method)
+struct NpzWriter {
+  FILE* f;
+  struct Entry { std::string name; uint32_t crc, size, offset; };
+  std::vector<Entry> entries;
+  explicit NpzWriter(const std::string& path) : f(std::fopen(path.c_str(), "wb")) {}
+  bool ok() const { return f != nullptr; }
+  static void le16(std::string& s, uint16_t v) { s.push_back((char)(v & 255)); s.push_back((char)(v >> 8)); }
+  static void le32(std::string& s, uint32_t v) { for (int i = 0; i < 4; i++) s.push_back((char)((v >> (8 * i)) & 255)); }
+  void add(const std::string& key, const char* descr, const std::vector<size_t>& shape, const void* data, size_t nbytes) {
+    std::string hdr = std::string("{'descr': '") + descr + "', 'fortran_order': False, 'shape': (";
+    for (size_t i = 0; i < shape.size(); i++) hdr += std::to_string(shape[i]) + (shape.size() == 1 || i + 1 < shape.size() ? "," : "");
+    hdr += "), }";
+    while ((10 + hdr.size() + 1) % 64 != 0) hdr.push_back(' ');
+    hdr.push_back('\n');
+    std::string npy("\x93NUMPY\x01\x00", 8);
+    le16(npy, (uint16_t)hdr.size());
+    npy += hdr;
+    const std::string name = key + ".npy";
+    uint32_t crc = crc32(0L, (const Bytef*)npy.data(), (uInt)npy.size());
+    crc = crc32(crc, (const Bytef*)data, (uInt)nbytes);
+    const uint32_t size = (uint32_t)(npy.size() + nbytes);
+    Entry e{name, crc, size, (uint32_t)std::ftell(f)};
+    std::string lh;
+    le32(lh, 0x04034b50); le16(lh, 20); le16(lh, 0); le16(lh, 0); le16(lh, 0); le16(lh, 0x21);
+    le32(lh, crc); le32(lh, size); le32(lh, size); le16(lh, (uint16_t)name.size()); le16(lh, 0);
+    lh += name;
+    std::fwrite(lh.data(), 1, lh.size(), f);
+    std::fwrite(npy.data(), 1, npy.size(), f);
+    std::fwrite(data, 1, nbytes, f);
+    entries.push_back(e);
+  }
+  void close() {
+    const uint32_t cd_off = (uint32_t)std::ftell(f);
+    std::string cd;
+    for (const auto& e : entries) {
+      le32(cd, 0x02014b50); le16(cd, 20); le16(cd, 20); le16(cd, 0); le16(cd, 0); le16(cd, 0); le16(cd, 0x21);
+      le32(cd, e.crc); le32(cd, e.size); le32(cd, e.size); le16(cd, (uint16_t)e.name.size()); le16(cd, 0); le16(cd, 0);
+      le16(cd, 0); le16(cd, 0); le32(cd, 0); le32(cd, e.offset);
+      cd += e.name;
+    }
+    std::string end;
+    le32(end, 0x06054b50); le16(end, 0); le16(end, 0); le16(end, (uint16_t)entries.size()); le16(end, (uint16_t)entries.size());
+    le32(end, (uint32_t)cd.size()); le32(end, cd_off); le16(end, 0);
+    std::fwrite(cd.data(), 1, cd.size(), f);
+    std::fwrite(end.data(), 1, end.size(), f);
+    std::fclose(f);
+    f = nullptr;
+  }
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    std::fprintf(stderr, "usage: %s <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.npz]\n", argv[0]);
+    return 2;
+  }
+  try {
+    maghost::RunConfig cfg = maghost::load_run_config(argv[1]);
+    std::vector<int32_t> list, devices;
+    int chunk = 2048;
+    std::string out_path;
+    bool dry_run = false;
+    for (int i = 2; i < argc; i++) {
+      const std::string a = argv[i];
+      if (a == "--dry-run") { dry_run = true; continue; }
+      if (a == "--devices" && i + 1 < argc) {
+        for (char* tok = std::strtok(argv[++i], ","); tok; tok = std::strtok(nullptr, ",")) devices.push_back(std::atoi(tok));
+      } else if (a == "--chunk" && i + 1 < argc) chunk = std::atoi(argv[++i]);
+      else if (a == "--out" && i + 1 < argc) out_path = argv[++i];
+      else list.push_back(std::atoi(a.c_str()));
+    }
+    if (cfg.input_file_name.empty()) throw std::runtime_error("input_file_name missing in io_parameters");
+    const maghost::MagnetizerInput in = maghost::load_magnetizer_input(cfg.input_file_name);
+    // jobs_reads_galaxy_list: ids are 1-based rows of the input file
+    if (list.empty()) for (int g = 1; g <= in.ngal; g++) list.push_back(g);
+    for (int g : list) if (g < 1 || g > in.ngal) throw std::runtime_error("galaxy id out of range: " + std::to_string(g));
+    const int ngal = (int)list.size(), nz = in.nz, nr = cfg.params.p_nx_ref;
+    std::vector<double> inputs((size_t)13 * ngal * nz);
+    for (int c = 0; c < 13; c++)
+      for (int k = 0; k < ngal; k++)
+        std::memcpy(&inputs[((size_t)c * ngal + k) * nz], &in.inputs[((size_t)c * in.ngal + (list[k] - 1)) * nz], sizeof(double) * nz);
+    // requested quantities (output_quantities_list; default: everything)
+    std::vector<int32_t> pq, sq;
+    std::vector<std::string> names = cfg.output_quantities_list;
+    if (names.empty()) { for (auto n : kProfileNames) names.push_back(n); for (auto n : kScalarNames) names.push_back(n); }
+    bool have_rkpc = false;
+    for (const auto& q : names) {
+      bool found = false;
+      for (int i = 0; i < MAG_NPROFILE; i++) if (q == kProfileNames[i]) { pq.push_back(i); found = true; if (i == MAG_Q_RKPC) have_rkpc = true; }
+      for (int i = 0; i < MAG_NSCALAR; i++) if (q == kScalarNames[i]) { sq.push_back(i); found = true; }
+      if (!found) std::fprintf(stderr, "warning: output quantity '%s' is not produced by this path; skipped\n", q.c_str());
+    }
+    if (!have_rkpc) pq.push_back(MAG_Q_RKPC);  // Output/r is always written (output.f90:56-60)
+    if (dry_run) {  // host-side logic only (parameter file, input file, galaxy list, quantity list): no device needed
+      std::printf("dry-run ngal %d nz %d list %zu p_courant_v %.17g p_nx_ref %d p_random_seed %d\n", in.ngal, nz, list.size(),
+                  cfg.params.p_courant_v, cfg.params.p_nx_ref, cfg.params.p_random_seed);
+      for (int c = 0; c < 13; c++) {
+        double sum = 0;
+        for (size_t k = 0; k < (size_t)ngal * nz; k++) sum += inputs[(size_t)c * ngal * nz + k];
+        std::printf("column %s sum %.17g\n", maghost::kInputColumns[c], sum);
+      }
+      std::printf("t %.17g .. %.17g\nprofiles", in.t_gyr.front(), in.t_gyr.back());
+      for (int q : pq) std::printf(" %s", kProfileNames[q]);
+      std::printf("\nscalars");
+      for (int q : sq) std::printf(" %s", kScalarNames[q]);
+      std::printf("\n");
+      return 0;
+    }
+    if (devices.empty()) {
+      int nd = 0;
+      if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) throw std::runtime_error("no CUDA device (there is no CPU fallback)");
+      for (int d = 0; d < nd; d++) devices.push_back(d);
+    }
+    std::vector<double> profiles((size_t)pq.size() * ngal * nz * nr), scalars((size_t)sq.size() * ngal * nz);
+    std::vector<char> status((size_t)ngal * nz);
+    std::vector<int32_t> nsteps(ngal), error(ngal), done(devices.size()), stolen(devices.size());
+    std::vector<int64_t> stages(ngal);
+    std::vector<uint32_t> flags(ngal);
+    mag_outputs_t out{profiles.data(), scalars.empty() ? nullptr : scalars.data(), status.data(), nsteps.data(), error.data(),
+                      stages.data(), flags.data()};
+    std::printf("Magnetizer (B200 path): '%s'  %d galaxies x %d snapshots, %zu GPU(s), chunk %d\n", cfg.model_name.c_str(), ngal, nz,
+                devices.size(), chunk);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = mag_solve_partitioned(&cfg.params, (int)devices.size(), devices.data(), ngal, list.data(), nz, in.t_gyr.data(),
+                                         inputs.data(), (int)pq.size(), pq.data(), (int)sq.size(), sq.data(), &out, chunk,
+                                         done.data(), stolen.data());
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
+    // ---- write_output (output.f90:23-236): unit conversion, [ngal][nx][nz] layout, Log group
+    if (out_path.empty()) {
+      out_path = cfg.output_file_name.empty() ? "magnetizer_b200_output.npz" : cfg.output_file_name;
+      const size_t dot = out_path.rfind('.');
+      out_path = (dot == std::string::npos ? out_path : out_path.substr(0, dot)) + ".npz";
+    }
+    NpzWriter w(out_path);
+    if (!w.ok()) throw std::runtime_error("cannot write " + out_path);
+    std::vector<double> tmp((size_t)ngal * nr * nz);
+    long long total_stages = 0;
+    for (auto s : stages) total_stages += s;
+    for (size_t q = 0; q < pq.size(); q++) {
+      const std::string name = kProfileNames[pq[q]];
+      const double fac = unit_factor(name);
+      const double* src = &profiles[q * (size_t)ngal * nz * nr];
+      for (int g = 0; g < ngal; g++)
+        for (int iz = 0; iz < nz; iz++)
+          for (int i = 0; i < nr; i++) {
+            const double v = src[((size_t)g * nz + iz) * nr + i];
+            tmp[((size_t)g * nr + i) * nz + iz] = (v == MAG_INVALID) ? v : v * fac;
+          }
+      if (name != "rkpc" || have_rkpc) w.add("Output/" + name, "<f8", {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data(), tmp.size() * 8);
+      if (name == "rkpc") w.add("Output/r", "<f8", {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data(), tmp.size() * 8);
+    }
+    for (size_t q = 0; q < sq.size(); q++)
+      w.add(std::string("Output/") + kScalarNames[sq[q]], "<f8", {(size_t)ngal, (size_t)nz}, &scalars[q * (size_t)ngal * nz], (size_t)ngal * nz * 8);
+    w.add("Log/status", "|S1", {(size_t)ngal, (size_t)nz}, status.data(), status.size());
+    std::vector<double> log_n(ngal), log_c(ngal), log_rt(ngal);
+    std::map<char, long> counts;
+    for (int g = 0; g < ngal; g++) {
+      log_n[g] = nsteps[g];
+      log_c[g] = error[g] ? 0.0 : 1.0;  // Log/completed is only written when runtime > 0 (distributor.f90:363)
+      log_rt[g] = total_stages > 0 ? secs * (double)stages[g] / (double)total_stages : 0.0;
+      for (int iz = 0; iz < nz; iz++) counts[status[(size_t)g * nz + iz]]++;
+    }
+    w.add("Log/nsteps", "<f8", {(size_t)ngal}, log_n.data(), log_n.size() * 8);
+    w.add("Log/completed", "<f8", {(size_t)ngal}, log_c.data(), log_c.size() * 8);
+    w.add("Log/runtime", "<f8", {(size_t)ngal}, log_rt.data(), log_rt.size() * 8);
+    w.add("Log/gal_id", "<i4", {(size_t)ngal}, list.data(), list.size() * 4);
+    w.add("Input/t", "<f8", {(size_t)nz}, in.t_gyr.data(), in.t_gyr.size() * 8);
+    w.close();
+    std::printf("  solved in %.3f s  (%.1f galaxies/s, %.3e point-stages/s)\n", secs, ngal / secs, total_stages / secs);
+    for (size_t d = 0; d < devices.size(); d++)
+      std::printf("  GPU %d: %d chunks (%d stolen)\n", devices[d], done[d], stolen[d]);
+    std::printf("  status codes:");
+    for (auto& kv : counts) std::printf(" '%c' x%ld", kv.first, kv.second);
+    std::printf("\n  wrote %s\n", out_path.c_str());
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "Magnetizer_b200: %s\n", e.what());
+    return 1;
+  }
+}

@@ -166,6 +166,40 @@ class DynamoSolver:
         _check(rc, "mag_solve_batch_device")
 
 
+def solve_partitioned(gal_ids, t_gyr, inputs, devices, chunk=2048, params: MagParams | None = None,
+                      profiles=PROFILE_NAMES, scalars=SCALAR_NAMES):
+    """Multi-GPU solve of one catalogue: static + work-stealing partition of galaxy chunks
+    over `devices` (mag_solve_partitioned; replaces jobs_distribute, distributor.f90:180).
+    Returns the same dict as DynamoSolver.run plus chunks_done / chunks_stolen per device."""
+    lib = load_library()
+    p = params if params is not None else default_params()
+    inputs = np.ascontiguousarray(inputs, np.float64)
+    t_gyr = np.ascontiguousarray(t_gyr, np.float64)
+    gal_ids = np.ascontiguousarray(gal_ids, np.int32)
+    _, ngal, nz = inputs.shape
+    pq = np.array([PROFILE_ID[q] for q in profiles], np.int32)
+    sq = np.array([SCALAR_ID[q] for q in scalars], np.int32)
+    nr = p.p_nx_ref
+    res = dict(profiles=np.empty((len(pq), ngal, nz, nr)), scalars=np.empty((len(sq), ngal, nz)),
+               status=np.empty((ngal, nz), np.uint8), nsteps=np.empty(ngal, np.int32), error=np.empty(ngal, np.int32),
+               point_stages=np.empty(ngal, np.int64), flags=np.empty(ngal, np.uint32))
+    o = MagOutputs(*[_ptr(res[k]) if res[k].size else None
+                     for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags")])
+    dev = np.ascontiguousarray(devices, np.int32)
+    done, stolen = np.zeros(dev.size, np.int32), np.zeros(dev.size, np.int32)
+    rc = lib.mag_solve_partitioned(C.byref(p), C.c_int32(dev.size), _ptr(dev), C.c_int32(ngal), _ptr(gal_ids), C.c_int32(nz),
+                                   _ptr(t_gyr), _ptr(inputs), C.c_int32(len(pq)), _ptr(pq), C.c_int32(len(sq)), _ptr(sq),
+                                   C.byref(o), C.c_int32(chunk), _ptr(done), _ptr(stolen))
+    if rc != 0:
+        lib.mag_partition_last_error.restype = C.c_char_p
+        raise MagnetizerError(f"mag_solve_partitioned failed: {ERROR_NAMES.get(rc, rc)}: "
+                              f"{lib.mag_partition_last_error().decode(errors='replace')}")
+    res["status"] = res["status"].view("S1")
+    res["profile_names"], res["scalar_names"] = tuple(profiles), tuple(scalars)
+    res["chunks_done"], res["chunks_stolen"] = done, stolen
+    return res
+
+
 # ---------------------------------------------------------------------------
 # write_output's unit table (reference source/output.f90:63-201; constants.f90:40-74).
 def _units():

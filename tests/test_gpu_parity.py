@@ -70,6 +70,17 @@ def test_device_det_math_bit_exact(solver, oracle):
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), which
 
 
+def test_device_fast_sqrt(solver):
+    """sqrt|alpha| of the hot loop (rsqrt seed + one Newton step): relative error < 1e-12."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([np.exp(rng.uniform(-60, 60, 200000)), -np.exp(rng.uniform(-20, 20, 1000)), [1.0, 4.0, 1e-300]])
+    got = np.empty_like(x)
+    assert solver._lib.mag_test_fast_sqrt(C.c_int32(x.size), _vp(x), _vp(got)) == 0
+    err = np.abs(got / np.sqrt(np.abs(x)) - 1)
+    print("fast_sqrt max rel err", err.max())
+    assert err.max() < 1e-12
+
+
 def test_single_galaxy_mode(solver, oracle, example_input):
     """BASELINE config 1: example input, single-galaxy mode, Fortran gal_id=1."""
     t, inputs = example_input
@@ -165,3 +176,19 @@ def test_linearity_property_of_kinematic_phase(solver, example_input):
     b = solver.run(ids[perm], t, np.ascontiguousarray(sub[:, perm, :]), profiles=("Br", "Bp"), scalars=("Bmax",))
     assert np.array_equal(a["profiles"][:, perm], b["profiles"])
     assert np.array_equal(a["status"][perm], b["status"])
+
+
+def test_partitioned_solve_matches_single_context(solver, example_input):
+    """mag_solve_partitioned (static + work-stealing chunks, one host thread per device,
+    host-side gather): two contexts on the same GPU must reproduce the single-context
+    result bit for bit, whatever thread ends up with which chunk."""
+    from magnetizer_b200.solver import solve_partitioned
+    t, inputs = example_input
+    ids, sub = _subset(inputs, list(range(30, 71)))
+    prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax", "dt")
+    one = solver.run(ids, t, sub, profiles=prof, scalars=scal)
+    two = solve_partitioned(ids, t, sub, devices=[0, 0], chunk=4, profiles=prof, scalars=scal)
+    assert two["chunks_done"].sum() == 11 and (two["chunks_done"] > 0).all()
+    for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
+        assert np.array_equal(one[k], two[k]), k
+    assert np.array_equal(one["status"], two["status"])
