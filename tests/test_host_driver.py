@@ -55,12 +55,11 @@ def test_no_cpu_fallback(exe):
 
 
 @pytest.mark.gpu
-def test_driver_end_to_end_example(exe, oracle, example_input):
+def test_driver_end_to_end_example(exe, oracle, example_input, tmp_path):
     """BASELINE configs 1/2 through the real file format: single-galaxy mode and a full run."""
     from parity import RTOL
     t, inputs = example_input
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    out = os.path.join(ROOT, "gpurun_out", "example_output.npz")
+    out = str(tmp_path / "example_output.npz")
     log = subprocess.check_output([exe, PARAMS, "--devices", "0,0", "--chunk", "16", "--out", out], cwd=ROOT, text=True)
     assert "196 galaxies x 40 snapshots" in log
     d = np.load(out)
@@ -76,7 +75,7 @@ def test_driver_end_to_end_example(exe, oracle, example_input):
     assert np.array_equal(d["Log/status"].view("S1").reshape(196, 40), ora["status"])
     assert np.array_equal(d["Log/nsteps"], ora["nsteps"].astype(float))
     # single-galaxy mode (Fortran gal_id = 1)
-    out1 = os.path.join(ROOT, "gpurun_out", "example_output_gal1.npz")
+    out1 = str(tmp_path / "example_output_gal1.npz")
     subprocess.check_call([exe, PARAMS, "1", "--out", out1], cwd=ROOT, stdout=subprocess.DEVNULL)
     d1 = np.load(out1)
     assert np.array_equal(d1["Output/Br"][0], d["Output/Br"][0]) and d1["Log/gal_id"].tolist() == [1]
