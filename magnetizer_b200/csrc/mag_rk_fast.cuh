@@ -33,7 +33,7 @@
 
 namespace magdev {
 
-#define MAG_FAST_BLK 8        // steps per checkpoint block
+#define MAG_FAST_BLK 16       // steps per checkpoint block
 #define MAG_TEAM 64           // threads per galaxy team
 #define MAG_FAST_MAXPPL 8     // fast path up to nx = 512
 #define MAG_LINE_S (4 * MAG_TEAM + 8)   // shared line of the PPL <= 4 variants
