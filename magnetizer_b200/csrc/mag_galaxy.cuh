@@ -21,6 +21,7 @@ namespace magdev {
 
 struct SnapRec;
 struct GalHead;
+struct ChainJob;
 
 // ------------------------------------------------------------------ workspace
 enum WsArray {
@@ -61,6 +62,12 @@ struct KernelArgs {
   double* arena;         // record arrays
   unsigned long long* arena_top;
   long long arena_cap;   // in doubles
+  // hydrostatic-chain jobs exchanged between the two profile passes and k_chains
+  ChainJob* jobs;        // [job_cap]
+  int32_t* job_count;
+  int32_t* jobidx;       // [chunk][nz][2] -> index into jobs or -1
+  int32_t job_cap;
+  int32_t chain_mode;    // CHAIN_MODE_* of this k_profiles launch
 };
 #define MAG_ERR_ARENA (-6)  // internal: record arena exhausted (the host retries with smaller chunks)
 
@@ -86,6 +93,9 @@ struct Gal {
   double t_last_sign_choice;
   bool refresh_sign, sign_valid;
   int sign_nx;
+  // hydrostatic chain handling (mag_phases.cuh): inline / export jobs / import results
+  int chain_mode, chain_it, chain_kind, chain_job;
+  bool chain_diverged;
   // status / stats
   char status;
   uint32_t flags;
@@ -313,28 +323,38 @@ __device__ inline double molecular_to_diffuse_ratio(const mag_params_t& P, doubl
   return detmath::det_pow(Pnot / P.p_Rmol_P0, P.p_Rmol_alpha);
 }
 
-// The serial chain over radius, executed by lane 0 (bracket of radius i+1 comes from the
-// root at radius i).  Returns false when the solve gave up (h = -1 everywhere).
-__device__ inline bool hydrostatic_chain_lane0(Gal& G, const double* r /*abs(r_kpc)*/) {
-  const mag_params_t& P = G.a->P;
-  const int n = G.nx, ng = MAG_NGHOST;
-  const double* Sigma_d = G.A(A_SIGD);
-  const double* Sigma_star = G.A(A_SIGS);
-  const double* Rm = G.A(A_RM);
-  const double *Om_h = G.A(A_OMH), *G_h = G.A(A_GH), *Om_b = G.A(A_OMB), *G_b = G.A(A_GB);
-  double* h_d = G.A(A_HKPC);
-  double* rho_d = G.A(A_RHO);
-  const double rs = MAG_DISK_SCALE_TO_HALFMASS * G.r_disk;
-  const double h_star = G.r_disk * MAG_DISK_SCALE_TO_HALFMASS * P.p_stellarHeightToRadiusScale;
-  const double h_m = G.r_disk * MAG_DISK_SCALE_TO_HALFMASS * P.p_molecularHeightToRadiusScale;
+// One hydrostatic-equilibrium chain (solve_hydrostatic_equilibrium_numerical,
+// pressureEquilibrium.f90:51-251): serial over radius (the bracket of radius i+1 comes from
+// the root at radius i), therefore executed by ONE thread: lane 0 of the galaxy's warp
+// (inline mode) or one thread per (galaxy, snapshot) job of k_chains, 32 chains per warp.
+struct ChainIn {
+  int n;                       // grid size
+  double r_disk, Mstars_bulge;
+  const double *r;             // abs(r_kpc)
+  const double *Sigma_d, *Sigma_star, *Rm, *Om_h, *G_h, *Om_b, *G_b;
+  double *h_d, *rho_d;         // out
+};
+#define CHAIN_OK 1        // the solve did not give up
+#define CHAIN_STATUS_P 2  // status 'P' was raised (log-extrapolated scale height)
+#define CHAIN_SECANT 4    // the secant fallback was used
+// Returns CHAIN_* bits.
+__device__ inline int hydro_chain(const mag_params_t& P, const ChainIn& c) {
+  const int n = c.n, ng = MAG_NGHOST;
+  const double *Sigma_d = c.Sigma_d, *Sigma_star = c.Sigma_star, *Rm = c.Rm;
+  const double *Om_h = c.Om_h, *G_h = c.G_h, *Om_b = c.Om_b, *G_b = c.G_b, *r = c.r;
+  double *h_d = c.h_d, *rho_d = c.rho_d;
+  int bits = 0;
+  const double rs = MAG_DISK_SCALE_TO_HALFMASS * c.r_disk;
+  const double h_star = c.r_disk * MAG_DISK_SCALE_TO_HALFMASS * P.p_stellarHeightToRadiusScale;
+  const double h_m = c.r_disk * MAG_DISK_SCALE_TO_HALFMASS * P.p_molecularHeightToRadiusScale;
   const double cs = P.p_ISM_sound_speed_km_s * 1e5;
   // computes_midplane_ISM_pressure_from_B_and_rho with B = 0 (pressureEquilibrium.f90:561-573)
   const double Kgas = (P.p_ISM_kappa / 3.0 * (1. + 2. * P.p_ISM_xi) + 1.0 / P.p_ISM_gamma) * (cs * cs);
   const double kmkpc2 = (1e3 / MAG_KPC_SI) * (1e3 / MAG_KPC_SI);
-  const bool use_bulge = P.p_use_Pbulge && G.Mstars_bulge > 1e3;
+  const bool use_bulge = P.p_use_Pbulge && c.Mstars_bulge > 1e3;
   const bool use_dm = P.p_use_Pdm != 0;
   int error_count = 0;
-  double minimum_h = 1e-3 * G.r_disk, maximum_h = 2.0 * G.r_disk, guess_h = (double)0.050f;
+  double minimum_h = 1e-3 * c.r_disk, maximum_h = 2.0 * c.r_disk, guess_h = (double)0.050f;
   bool gave_up = false;
   for (int i = ng + 2; i <= n && !gave_up; i++) {
     const int k = i - 1;
@@ -366,11 +386,11 @@ __device__ inline bool hydrostatic_chain_lane0(Gal& G, const double* r /*abs(r_k
     if (signbit(pe_min) != signbit(pe_max)) {
       if (!brent_root(pe, minimum_h, maximum_h, &root)) { gave_up = true; break; }
     } else {
-      G.flags |= MAG_FLAG_SECANT;
+      bits |= CHAIN_SECANT;
       const bool ok = secant_root(pe, guess_h, 1e-6, &root);
       if (!ok || root < 0) {
         if (error_count < 4 && i > ng + 2 + 2) {
-          G.status = 'P';
+          bits |= CHAIN_STATUS_P;
           double e = (detmath::det_log(h_d[k - 1]) - detmath::det_log(h_d[k - 2])) / (r[k - 1] - r[k - 2]) * (r[k] - r[k - 1]);
           e = e + detmath::det_log(h_d[k - 1]);
           root = detmath::det_exp(e);
@@ -395,13 +415,23 @@ __device__ inline bool hydrostatic_chain_lane0(Gal& G, const double* r /*abs(r_k
   }
   if (gave_up) {
     for (int j = 0; j < n; j++) { h_d[j] = -1; rho_d[j] = 0.0; }
-    return false;
+    return bits;
   }
   for (int i = 1; i <= ng; i++) h_d[i - 1] = h_d[2 * ng + 2 - i - 1];
   h_d[ng] = h_d[ng + 1] + (r[ng] - r[ng + 1]) * (h_d[ng + 1] - h_d[ng + 2]) / (r[ng + 1] - r[ng + 2]);
   for (int i = 1; i <= ng + 1; i++) rho_d[i - 1] = density_to_scaleheight(h_d[i - 1], Sigma_d[i - 1]);
-  return true;
+  return bits | CHAIN_OK;
 }
+
+#define CHAIN_MODE_INLINE 0
+#define CHAIN_MODE_EXPORT 1
+#define CHAIN_MODE_IMPORT 2
+struct Gal;
+__device__ void chain_export(Gal& G, const double* absr, uint32_t rot_flags);   // mag_phases.cuh
+__device__ int chain_lookup(Gal& G);                          // job of the current construct_profiles call or -1
+__device__ const double* chain_job_array(const Gal& G, int k);
+__device__ uint32_t chain_job_flags(const Gal& G);
+__device__ int chain_import(Gal& G);                          // < 0: not available
 
 // ------------------------------------------------------------------ construct_profiles
 // profiles.f90:33-272 (B absent).  Also prepares what set_timestep needs (min h>0, max
@@ -435,12 +465,23 @@ __device__ inline bool construct_profiles(Gal& G) {
   double best = CUDART_INF; int ireg = 0x7fffffff;
   double bestm = CUDART_INF; int ihalf = 0x7fffffff;
   uint32_t fl = 0;
+  // pass 2 of the profile phase re-uses the rotation curves pass 1 computed for this very
+  // grid and snapshot (the halo contraction -- one Brent solve per radius -- dominates the cost)
+  G.chain_job = (G.chain_mode == CHAIN_MODE_IMPORT) ? chain_lookup(G) : -1;
+  const double* cached = (G.chain_job >= 0) ? chain_job_array(G, 10) : nullptr;   // Om_d, Om_b, Om_h before regularisation
+  if (cached && lane == 0) fl = chain_job_flags(G);
+  double *raw_b = G.A(A_T1), *raw_h = G.A(A_T2);
   for (int i = lane; i < nx; i += 32) {
     const double r = rk[i];
-    Om_d[i] = disk_omega(c, r);
-    Om_b[i] = bulge_omega(c, r);
     double oh = 0.0;
-    if (with_halo) oh = halo_velocity_contracted(c, fabs(r), Om_d[i], Om_b[i], i == MAG_NGHOST, &fl) / r;
+    if (cached) {
+      Om_d[i] = cached[i]; Om_b[i] = cached[nx + i]; oh = cached[2 * nx + i];
+    } else {
+      Om_d[i] = disk_omega(c, r);
+      Om_b[i] = bulge_omega(c, r);
+      if (with_halo) oh = halo_velocity_contracted(c, fabs(r), Om_d[i], Om_b[i], i == MAG_NGHOST, &fl) / r;
+    }
+    raw_b[i] = Om_b[i]; raw_h[i] = oh;
     Om_h[i] = oh;
     Omk[i] = sqrt(Om_d[i] * Om_d[i] + Om_b[i] * Om_b[i] + oh * oh);
     const double d = fabs(r - rreg);
@@ -507,15 +548,28 @@ __device__ inline bool construct_profiles(Gal& G) {
     }
   }
   __syncwarp();
-  int okc = 1;
-  uint32_t fl0 = G.flags; char st0 = G.status;
-  if (lane == 0) {
-    okc = hydrostatic_chain_lane0(G, absr) ? 1 : 0;
-    fl0 = G.flags; st0 = G.status;
+  // ---- the hydrostatic chain: exported as a job (profile pass 1), imported from the job's
+  // results (pass 2), or solved inline by lane 0
+  if (G.chain_mode == CHAIN_MODE_EXPORT) {
+    chain_export(G, absr, fl);
+    return true;   // pass 1 only walks the grid recurrence; pass 2 finishes the snapshot
   }
-  okc = __shfl_sync(FULL, okc, 0);
-  G.flags = __shfl_sync(FULL, fl0, 0);
-  G.status = (char)__shfl_sync(FULL, (int)st0, 0);
+  int bits = -1;
+  if (G.chain_mode == CHAIN_MODE_IMPORT) bits = chain_import(G);
+  if (bits < 0) {
+    if (lane == 0) {
+      ChainIn c;
+      c.n = nx; c.r_disk = G.r_disk; c.Mstars_bulge = G.Mstars_bulge; c.r = absr;
+      c.Sigma_d = Sigma_d; c.Sigma_star = Sigma_star; c.Rm = Rm;
+      c.Om_h = Om_h; c.G_h = G_h; c.Om_b = Om_b; c.G_b = G_b;
+      c.h_d = G.A(A_HKPC); c.rho_d = G.A(A_RHO);
+      bits = hydro_chain(P, c);
+    }
+    bits = __shfl_sync(FULL, bits, 0);
+  }
+  const int okc = (bits & CHAIN_OK) ? 1 : 0;
+  if (bits & CHAIN_SECANT) G.flags |= MAG_FLAG_SECANT;
+  if (bits & CHAIN_STATUS_P) G.status = 'P';
   __syncwarp();
   double *h_kpc = G.A(A_HKPC), *rho = G.A(A_RHO);
   if (!okc) {  // any(h_kpc<0)

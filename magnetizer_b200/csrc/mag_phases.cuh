@@ -49,6 +49,17 @@ struct GalHead {       // [ngal]
   long long cost;      // sum over SR_SOLVE snapshots of nsteps*nx
 };
 
+struct ChainJob {      // one hydrostatic chain = one construct_profiles call of one galaxy
+  // arena offset of CHAIN_JOB_ARRAYS arrays of nx doubles: |r|, Sigma_d, Sigma_*, Rm, Om_h, G_h, Om_b, G_b (chain
+  // inputs), h, rho (chain outputs), Om_d, Om_b, Om_h before regularisation (rotation curves)
+  long long off;
+  int32_t nx, bits;    // bits: CHAIN_* result of k_chains
+  uint32_t rot_flags;  // MAG_FLAG_* raised by the rotation curves
+  int32_t pad;
+  double r_disk, Mstars_bulge;
+  double r_max_kpc, dr_kpc;   // with nx and r_disk: identifies the grid the job was exported on
+};
+
 __device__ inline long long arena_alloc(const KernelArgs* a, int lane, long long n) {
   long long off = -1;
   if (lane == 0) {
@@ -56,6 +67,84 @@ __device__ inline long long arena_alloc(const KernelArgs* a, int lane, long long
     if (off + n > a->arena_cap) { atomicExch(a->fail, MAG_ERR_ARENA); off = -1; }
   }
   return __shfl_sync(FULL, off, 0);
+}
+
+// ---- hydrostatic chains as jobs.  Pass 1 of the profile phase (k_profiles, CHAIN_MODE_EXPORT)
+// walks the grid recurrence of every galaxy assuming that each chain succeeds and exports the
+// inputs of every chain; k_chains then solves 32 chains per warp (one thread each) instead of
+// one chain on lane 0 of a warp; pass 2 (CHAIN_MODE_IMPORT) repeats the walk with the chain
+// results and finishes the snapshots.  If a chain fails in a way that changes the walk
+// (the pre-adjust solve of a snapshot that leaves an elliptical phase), pass 2 notices that
+// the job it needs does not exist or has another grid size and solves inline from there on.
+#define CHAIN_JOB_ARRAYS 13
+__device__ void chain_export(Gal& G, const double* absr, uint32_t rot_flags) {
+  const KernelArgs* a = G.a;
+  const int nx = G.nx, lane = G.lane;
+  const long long off = arena_alloc(a, lane, (long long)CHAIN_JOB_ARRAYS * nx);
+  int j = -1;
+  if (off >= 0 && lane == 0) {
+    j = atomicAdd(a->job_count, 1);
+    if (j >= a->job_cap) { atomicExch(a->fail, MAG_ERR_ARENA); j = -1; }
+  }
+  j = __shfl_sync(FULL, j, 0);
+  if (j < 0) return;
+  const int src[CHAIN_JOB_ARRAYS] = {-1, A_SIGD, A_SIGS, A_RM, A_OMH, A_GH, A_OMB, A_GB, -2, -2, A_OMD, A_T1, A_T2};
+  for (int k = 0; k < CHAIN_JOB_ARRAYS; k++) {
+    if (src[k] == -2) continue;
+    const double* s = (k == 0) ? absr : G.A(src[k]);
+    double* d = a->arena + off + (long long)k * nx;
+    for (int i = lane; i < nx; i += 32) d[i] = s[i];
+  }
+  if (lane == 0) {
+    ChainJob J;
+    J.off = off; J.nx = nx; J.bits = 0; J.r_disk = G.r_disk; J.Mstars_bulge = G.Mstars_bulge;
+    J.r_max_kpc = G.r_max_kpc; J.dr_kpc = G.dr_kpc; J.rot_flags = rot_flags; J.pad = 0;
+    a->jobs[j] = J;
+    a->jobidx[((size_t)(G.g - a->g0) * a->nz + (G.chain_it - 1)) * 2 + G.chain_kind] = j;
+  }
+  __syncwarp();
+}
+
+__device__ int chain_lookup(Gal& G) {
+  const KernelArgs* a = G.a;
+  if (G.chain_diverged) return -1;
+  const int j = a->jobidx[((size_t)(G.g - a->g0) * a->nz + (G.chain_it - 1)) * 2 + G.chain_kind];
+  if (j < 0) { G.chain_diverged = true; return -1; }
+  const ChainJob J = a->jobs[j];
+  if (J.nx != G.nx || J.r_disk != G.r_disk || J.r_max_kpc != G.r_max_kpc || J.dr_kpc != G.dr_kpc) {
+    G.chain_diverged = true;   // pass 1 walked another grid (it assumed a chain success that did not happen)
+    return -1;
+  }
+  return j;
+}
+__device__ const double* chain_job_array(const Gal& G, int k) {
+  const ChainJob& J = G.a->jobs[G.chain_job];
+  return G.a->arena + J.off + (long long)k * J.nx;
+}
+__device__ uint32_t chain_job_flags(const Gal& G) { return G.a->jobs[G.chain_job].rot_flags; }
+
+__device__ int chain_import(Gal& G) {
+  const KernelArgs* a = G.a;
+  if (G.chain_job < 0) return -1;
+  const ChainJob J = a->jobs[G.chain_job];
+  const double *h = a->arena + J.off + 8LL * J.nx, *rho = h + J.nx;
+  double *hd = G.A(A_HKPC), *rd = G.A(A_RHO);
+  for (int i = G.lane; i < J.nx; i += 32) { hd[i] = h[i]; rd[i] = rho[i]; }
+  __syncwarp();
+  return J.bits;
+}
+
+// one chain job, one thread (k_chains)
+__device__ inline void run_chain_job(const KernelArgs& a, int j) {
+  ChainJob& J = a.jobs[j];
+  const int nx = J.nx;
+  double* base = a.arena + J.off;
+  ChainIn c;
+  c.n = nx; c.r_disk = J.r_disk; c.Mstars_bulge = J.Mstars_bulge;
+  c.r = base; c.Sigma_d = base + nx; c.Sigma_star = base + 2LL * nx; c.Rm = base + 3LL * nx;
+  c.Om_h = base + 4LL * nx; c.G_h = base + 5LL * nx; c.Om_b = base + 6LL * nx; c.G_b = base + 7LL * nx;
+  c.h_d = base + 8LL * nx; c.rho_d = base + 9LL * nx;
+  J.bits = hydro_chain(a.P, c);
 }
 
 // writes the record of snapshot `it` from the warp's workspace
@@ -87,13 +176,15 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
   const bool test_run = P.p_no_magnetic_fields_test_run != 0;
   const int lane = G.lane;
   bool elliptical = false;
+  const bool exporting = G.a->chain_mode == CHAIN_MODE_EXPORT;   // pass 1: no outputs, no records
+  G.chain_mode = G.a->chain_mode; G.chain_diverged = false; G.chain_kind = 0;
   G.status = test_run ? 't' : 'M';
   G.flags = 0; G.point_stages = 0;
   G.last_output = false;
   G.t = 0; G.dt = 0; G.nsteps = 20; G.time_between_inputs = 0; G.minh = 1e10; G.maxetat = 0; G.tau_min = 0;
   G.t_last_sign_choice = 0; G.refresh_sign = true; G.sign_nx = -1;
   H.cost = 0; H.flags = 0; H.error = 0;
-  reset_outputs(G);
+  if (!exporting) reset_outputs(G);
   load_input_parameters(G);
   H.init_it = G.init_it; H.max_it = G.max_it;
   if (set_input_params(G)) return true;
@@ -107,6 +198,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
     }
     __syncwarp();
   }
+  G.chain_it = G.init_it;
   bool able = construct_profiles(G);
   int it = G.init_it;
   if (!able) {  // finish()
@@ -127,12 +219,17 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
       fl |= SR_TRAP;
     } else {
       if (elliptical) {
+        G.chain_it = it; G.chain_kind = 1;
         able = construct_profiles(G);
-        off_pre = arena_alloc(G.a, lane, nx_pre);
-        if (off_pre < 0) return true;
-        const double* beq = G.A(A_BEQ);
-        for (int i = lane; i < nx_pre; i += 32) G.a->arena[off_pre + i] = beq[i];
-        __syncwarp();
+        G.chain_kind = 0;
+        if (!able) G.chain_diverged = true;   // pass 1 assumed success: its later jobs belong to another walk
+        if (!exporting) {
+          off_pre = arena_alloc(G.a, lane, nx_pre);
+          if (off_pre < 0) return true;
+          const double* beq = G.A(A_BEQ);
+          for (int i = lane; i < nx_pre; i += 32) G.a->arena[off_pre + i] = beq[i];
+          __syncwarp();
+        }
         fl |= SR_RESEED;
       }
       if (able) elliptical = false;
@@ -144,6 +241,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
         return true;
       }
       fl |= SR_ADJUSTED | (scaled ? SR_SCALEBACK : 0) | (extended ? SR_EXTEND : 0);
+      G.chain_it = it;
       able = construct_profiles(G);
       if (!able) {
         const bool okw = write_record(G, it, fl | SR_FAIL, nx_pre, nx_mid, off_pre);
@@ -158,8 +256,10 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
       H.cost += (long long)G.nsteps * G.nx;
     }
     if (G.last_output) fl |= SR_LAST;
-    if (!write_record(G, it, fl, nx_pre, nx_mid, off_pre)) return true;
-    write_profile_rows(G, it);
+    if (!exporting) {
+      if (!write_record(G, it, fl, nx_pre, nx_mid, off_pre)) return true;
+      write_profile_rows(G, it);
+    }
     if (G.last_output) break;
     G.status = test_run ? 't' : 'M';
     if (set_input_params(G)) break;

@@ -57,7 +57,7 @@ __global__ void __maxnreg__(MAG_PROFILE_MAXREG) k_profiles(KernelArgs a) {
     const bool err = run_profiles(G, H);
     H.error = err ? 1 : 0;
     if (err) H.cost = 0;
-    if (lane == 0) {
+    if (lane == 0 && a.chain_mode != CHAIN_MODE_EXPORT) {
       a.heads[q] = H;
       if (a.out.error) a.out.error[G.g] = H.error;
       if (err) {  // nothing else is written for this galaxy (dynamo.f90:69-73)
@@ -68,6 +68,14 @@ __global__ void __maxnreg__(MAG_PROFILE_MAXREG) k_profiles(KernelArgs a) {
     }
     __syncwarp();
   }
+}
+
+// ------------------------------------------------------------------ hydrostatic chains
+// One thread per chain job exported by pass 1 of the profile phase: 32 serial root-finder
+// chains per warp instead of one on lane 0.
+__global__ void __launch_bounds__(128) k_chains(KernelArgs a) {
+  const int n = *a.job_count < a.job_cap ? *a.job_count : a.job_cap;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) run_chain_job(a, j);
 }
 
 // ------------------------------------------------------------------ Phase B kernel
@@ -156,6 +164,10 @@ struct mag_ctx {
   unsigned long long* d_arena_top = nullptr;
   int* d_hist = nullptr;
   int* d_order = nullptr;
+  ChainJob* d_jobs = nullptr;
+  int* d_jobidx = nullptr;
+  int* d_job_count = nullptr;
+  int split_chains = 1;       // 1: two profile passes + k_chains, 0: chains inline on lane 0
   SnapRec* d_recs = nullptr;
   GalHead* d_heads = nullptr;
   int chunk_cap = 0;          // galaxies the record tables are sized for
@@ -230,6 +242,8 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   c->P = *params;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  const char* env_split = getenv("MAG_INLINE_CHAINS");
+  c->split_chains = (env_split && env_split[0] == '1') ? 0 : 1;
   const char* env_fast = getenv("MAG_DISABLE_FAST_PATH");
   c->use_fast = (env_fast && env_fast[0] == '1') ? 0 : 1;
   const size_t smemB = sizeof(RkShared);
@@ -256,6 +270,7 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   CUDA_TRY(cudaMalloc(&c->d_counter, 4 * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->d_arena_top, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&c->d_hist, COST_BUCKETS * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_job_count, sizeof(int)));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
   *ctx_out = c;
@@ -267,6 +282,7 @@ void mag_destroy(mag_ctx_t* c) {
   cudaSetDevice(c->device);
   cudaFree(c->wsA); cudaFree(c->wsB); cudaFree(c->d_counter); cudaFree(c->d_arena_top); cudaFree(c->d_hist);
   cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena);
+  cudaFree(c->d_jobs); cudaFree(c->d_jobidx); cudaFree(c->d_job_count);
   cudaFree(c->d_stage);
   for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -286,22 +302,28 @@ static int check_quantities(int32_t n_profile_q, const int32_t* profile_q, int32
 // fit is solved in several chunks, and a chunk that overflows the arena is reported as
 // MAG_ERR_CUDA with an explanatory message.
 #define ARENA_NX_BUDGET 176
-static long long arena_need(int chunk, int nz) { return (long long)chunk * nz * R_COUNT * ARENA_NX_BUDGET; }
+#define ARENA_ARRAYS (R_COUNT + CHAIN_JOB_ARRAYS + 1)   // record arrays + the arrays of a chain job (+ seeds of reseeded snapshots)
+static long long arena_need(int chunk, int nz) { return (long long)chunk * nz * ARENA_ARRAYS * ARENA_NX_BUDGET; }
 
 static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
   if (c->chunk_cap > 0 && nz <= c->nz_cap && (ngal <= c->chunk_cap)) { *chunk_out = ngal; return MAG_OK; }
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  free_b += (size_t)c->arena_cap * sizeof(double) + (size_t)c->chunk_cap * ((size_t)c->nz_cap * sizeof(SnapRec) + sizeof(GalHead) + sizeof(int));
+  free_b += (size_t)c->arena_cap * sizeof(double) +
+            (size_t)c->chunk_cap * ((size_t)c->nz_cap * (sizeof(SnapRec) + 2 * sizeof(ChainJob) + 2 * sizeof(int)) + sizeof(GalHead) + sizeof(int));
   const char* env = getenv("MAG_ARENA_FRACTION");
   const double frac = env ? atof(env) : 0.5;
-  const size_t per_gal = (size_t)nz * sizeof(SnapRec) + sizeof(GalHead) + sizeof(int) + (size_t)arena_need(1, nz) * sizeof(double);
+  const size_t per_gal = (size_t)nz * (sizeof(SnapRec) + 2 * sizeof(ChainJob) + 2 * sizeof(int)) + sizeof(GalHead) + sizeof(int) +
+                         (size_t)arena_need(1, nz) * sizeof(double);
   long long chunk = (long long)((double)free_b * frac / (double)per_gal);
   if (chunk > ngal) chunk = ngal;
   if (chunk < 1) { set_error("not enough device memory for the snapshot records"); return MAG_ERR_CUDA; }
   if (chunk <= c->chunk_cap && nz <= c->nz_cap) { *chunk_out = (int)chunk; return MAG_OK; }
-  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena);
-  c->d_order = nullptr; c->d_recs = nullptr; c->d_heads = nullptr; c->d_arena = nullptr; c->chunk_cap = 0; c->arena_cap = 0;
+  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena); cudaFree(c->d_jobs); cudaFree(c->d_jobidx);
+  c->d_order = nullptr; c->d_recs = nullptr; c->d_heads = nullptr; c->d_arena = nullptr; c->d_jobs = nullptr; c->d_jobidx = nullptr;
+  c->chunk_cap = 0; c->arena_cap = 0;
+  CUDA_TRY(cudaMalloc(&c->d_jobs, (size_t)chunk * nz * 2 * sizeof(ChainJob)));
+  CUDA_TRY(cudaMalloc(&c->d_jobidx, (size_t)chunk * nz * 2 * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->d_order, (size_t)chunk * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->d_recs, (size_t)chunk * nz * sizeof(SnapRec)));
   CUDA_TRY(cudaMalloc(&c->d_heads, (size_t)chunk * sizeof(GalHead)));
@@ -334,6 +356,7 @@ static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int3
   a.counter = c->d_counter; a.fail = c->d_counter + 1; a.replays = c->d_counter + 2; a.counter2 = c->d_counter + 3;
   a.use_fast = c->use_fast;
   a.recs = c->d_recs; a.heads = c->d_heads; a.arena = c->d_arena; a.arena_top = c->d_arena_top; a.arena_cap = c->arena_cap;
+  a.jobs = c->d_jobs; a.job_count = c->d_job_count; a.jobidx = c->d_jobidx;
   for (int g0 = 0; g0 < ngal; g0 += chunk) {
     const int n = (ngal - g0 < chunk) ? ngal - g0 : chunk;
     a.g0 = g0; a.g1 = g0 + n;
@@ -345,6 +368,20 @@ static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int3
     int ctasA = c->sm_count * c->ctasA_per_sm;
     const int needA = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (needA < ctasA) ctasA = needA;
+    a.job_cap = n * nz * 2;
+    if (c->split_chains) {
+      // pass 1: walk the grid recurrence, export the hydrostatic chains; then 32 chains per warp
+      CUDA_TRY(cudaMemsetAsync(c->d_job_count, 0, sizeof(int), st));
+      CUDA_TRY(cudaMemsetAsync(c->d_jobidx, 0xFF, (size_t)n * nz * 2 * sizeof(int), st));
+      a.chain_mode = CHAIN_MODE_EXPORT;
+      k_profiles<<<ctasA, WARPS_PER_CTA * 32, 0, st>>>(a);
+      k_chains<<<c->sm_count * 8, 128, 0, st>>>(a);
+      CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
+      a.chain_mode = CHAIN_MODE_IMPORT;
+      launches += 2;
+    } else {
+      a.chain_mode = CHAIN_MODE_INLINE;
+    }
     k_profiles<<<ctasA, WARPS_PER_CTA * 32, 0, st>>>(a);
     const int tb = 256, gb = (n + tb - 1) / tb;
     k_cost_hist<<<gb, tb, 0, st>>>(c->d_heads, n, c->d_hist);
