@@ -244,6 +244,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
       G.chain_it = it;
       able = construct_profiles(G);
       if (!able) {
+        if (G.last_output) fl |= SR_LAST;
         const bool okw = write_record(G, it, fl | SR_FAIL, nx_pre, nx_mid, off_pre);
         write_profile_rows(G, it);
         H.flags = G.flags;
@@ -339,6 +340,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
     G.dt = R.dt; G.nsteps = R.nsteps; G.t_Gyr = R.t_Gyr;
     G.status = (char)R.status;
     if (R.flags & SR_ADJUSTED) impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
+    if (!(R.flags & SR_LAST)) G.t = 0;  // set_input_params resets t except at the last snapshot (input_parameters.f90:224-233)
     if (R.flags & SR_FAIL) {  // finish() is the only writer of this snapshot
       estimate_Bzmod(G);
       write_field_rows(G, it);
@@ -348,7 +350,6 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
       init_seed_field(G);
       impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
     }
-    if (!(R.flags & SR_LAST)) G.t = 0;  // set_input_params resets t except at the last snapshot (input_parameters.f90:224-233)
     {  // f_snapshot_beginning = f
       for (int v = 0; v < 3; v++) {
         const double* f = G.A(A_F0 + v); double* fb = G.A(A_FB0 + v);

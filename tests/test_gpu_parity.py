@@ -157,13 +157,17 @@ def test_synthetic_histories_parity(solver, oracle, example_input):
     1290 so that the int32 wrap of igal**3 (random.f90:43) is exercised."""
     from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
     t, inputs = example_input
-    first, n = 2000, 48
-    syn = synthetic_histories(inputs, n, first=first)
-    ids = galaxy_ids(n, first=first)
-    prof, scal = ("Br", "Bp", "alp_m", "h", "n", "Omega", "Shear"), ("Bmax", "Bmax_idx", "dt")
-    gpu = solver.run(ids, t, syn, profiles=prof, scalars=scal)
-    ora = oracle.solve_batch(solver.params, ids, t, syn, profiles=prof, scalars=scal)
-    compare(gpu, ora)
+    prof, scal = ("Br", "Bp", "alp_m", "h", "n", "Omega", "Shear", "alp"), ("Bmax", "Bmax_idx", "dt")
+    # 2000..: plain slice; 1500..: contains a galaxy whose hydrostatic solve fails (status 'H',
+    # construct_profiles -> finish(), dynamo.f90:134-137) and secant-fallback cases
+    for first, n in ((2000, 48), (1500, 32)):
+        syn = synthetic_histories(inputs, n, first=first)
+        ids = galaxy_ids(n, first=first)
+        gpu = solver.run(ids, t, syn, profiles=prof, scalars=scal)
+        ora = oracle.solve_batch(solver.params, ids, t, syn, profiles=prof, scalars=scal)
+        compare(gpu, ora)
+        if first == 1500:
+            assert b"H" in ora["status"].tobytes()
 
 
 def test_linearity_property_of_kinematic_phase(solver, example_input):
@@ -192,3 +196,28 @@ def test_partitioned_solve_matches_single_context(solver, example_input):
     for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
         assert np.array_equal(one[k], two[k]), k
     assert np.array_equal(one["status"], two["status"])
+
+
+def test_unstable_timestep_blow_up_and_retry_path(oracle, example_input):
+    """Courant factors of 0.5 make the explicit scheme unstable: check_f_error trips, the
+    retry loop runs (status 'm', nsteps_0 steps, dynamo.f90:222-242) and the run ends with
+    status 'i' and a reseeded field (:245-257).  Exercises the checkpoint/replay logic of the
+    fast path (the blow-up must be detected at the reference's step and stage, otherwise the
+    accumulated time, the RNG stream and the reseeded field differ) and the invalidation of
+    the rows written by the profile phase for the snapshots that are never reached."""
+    from magnetizer_b200.solver import DynamoSolver
+    t, inputs = example_input
+    ids, sub = _subset(inputs, [1, 3, 24, 60, 101, 150])
+    p = oracle.default_params()
+    p.p_courant_v = 0.5
+    p.p_courant_eta = 0.5
+    s = DynamoSolver(params=p, device=0)
+    try:
+        gpu = s.run(ids, t, sub)
+        replays = s.info()["fast_path_replays"]
+    finally:
+        s.close()
+    ora = oracle.solve_batch(p, ids, t, sub)
+    assert b"i" in ora["status"].tobytes() and (ora["flags"] & 4).any()   # the case really blows up
+    compare(gpu, ora)
+    assert replays > 0
