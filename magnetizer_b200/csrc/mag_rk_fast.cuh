@@ -34,7 +34,13 @@
 namespace magdev {
 
 #define MAG_FAST_BLK 16       // steps per checkpoint block
-#define MAG_TEAM 64           // threads per galaxy team
+// Threads per galaxy team.  The library is built twice from the same sources: MAG_TEAM = 64
+// (libmagnetizer_b200.so: two points per thread on the default grid, nx = 107) and
+// MAG_TEAM = 128 (libmagnetizer_b200_team128.so, for grids of more than 256 points, e.g.
+// p_nx_ref = 401 of BASELINE config 5); mag_create of the first forwards to the second.
+#ifndef MAG_TEAM
+#define MAG_TEAM 64
+#endif
 #define MAG_FAST_MAXPPL 8     // fast path up to nx = 512
 #define MAG_LINE_S (4 * MAG_TEAM + 8)   // shared line of the PPL <= 4 variants
 #define MAG_LINE_L (8 * MAG_TEAM + 8)   // shared line of the PPL = 8 variant

@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "mag_galaxy.cuh"
 #include "mag_phases.cuh"
 #include "mag_rk_fast.cuh"
@@ -183,7 +185,53 @@ struct mag_ctx {
   int last_launches = 0;
   int last_replays = 0;
   int use_fast = 1;
+  // forwarding to the MAG_TEAM = 128 build of this library for grids of more than 256 points
+  void* fwd_lib = nullptr;
+  mag_ctx* fwd_ctx = nullptr;
 };
+
+#if MAG_TEAM == 64
+namespace {
+struct FwdApi {
+  int (*create)(const mag_params_t*, int, mag_ctx_t**);
+  void (*destroy)(mag_ctx_t*);
+  int (*solve)(mag_ctx_t*, int32_t, const int32_t*, int32_t, const double*, const double*, int32_t, const int32_t*, int32_t,
+               const int32_t*, const mag_outputs_t*);
+  int (*solve_dev)(mag_ctx_t*, int32_t, const int32_t*, int32_t, const double*, const double*, int32_t, const int32_t*, int32_t,
+                   const int32_t*, const mag_outputs_t*, void*);
+  int (*timing)(mag_ctx_t*, double*);
+  double (*peak)(mag_ctx_t*, int);
+  int (*info)(mag_ctx_t*, int32_t*);
+  int (*set_fast)(mag_ctx_t*, int32_t);
+  const char* (*last_error)(void);
+};
+FwdApi g_fwd;
+void* open_big_team_library() {
+  Dl_info di;
+  if (!dladdr((void*)&open_big_team_library, &di) || !di.dli_fname) return nullptr;
+  std::string path(di.dli_fname);
+  const size_t slash = path.rfind('/');
+  path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/libmagnetizer_b200_team128.so";
+  void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (!h) return nullptr;
+  g_fwd.create = (decltype(g_fwd.create))dlsym(h, "mag_create");
+  g_fwd.destroy = (decltype(g_fwd.destroy))dlsym(h, "mag_destroy");
+  g_fwd.solve = (decltype(g_fwd.solve))dlsym(h, "mag_solve_batch");
+  g_fwd.solve_dev = (decltype(g_fwd.solve_dev))dlsym(h, "mag_solve_batch_device");
+  g_fwd.timing = (decltype(g_fwd.timing))dlsym(h, "mag_last_timing");
+  g_fwd.peak = (decltype(g_fwd.peak))dlsym(h, "mag_measure_fp64_peak");
+  g_fwd.info = (decltype(g_fwd.info))dlsym(h, "mag_ctx_info");
+  g_fwd.set_fast = (decltype(g_fwd.set_fast))dlsym(h, "mag_set_fast_path");
+  g_fwd.last_error = (decltype(g_fwd.last_error))dlsym(h, "mag_last_error");
+  if (!g_fwd.create || !g_fwd.destroy || !g_fwd.solve || !g_fwd.solve_dev || !g_fwd.timing || !g_fwd.peak || !g_fwd.info ||
+      !g_fwd.set_fast || !g_fwd.last_error) { dlclose(h); return nullptr; }
+  return h;
+}
+}  // namespace
+#define MAG_FWD(c, call) if ((c) && (c)->fwd_ctx) return call
+#else
+#define MAG_FWD(c, call)
+#endif
 
 extern "C" {
 
@@ -238,6 +286,19 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) { set_error("kernels are built for sm_100a only"); return MAG_ERR_NO_DEVICE; }
+#if MAG_TEAM == 64
+  if (params->p_nx_ref + 2 * MAG_NGHOST > 4 * MAG_TEAM) {
+    // more than 256 grid points: use the 128-thread-team build if it is there (same ABI)
+    if (void* h = open_big_team_library()) {
+      mag_ctx* w = new mag_ctx();
+      w->P = *params; w->device = device; w->fwd_lib = h;
+      const int rc = g_fwd.create(params, device, &w->fwd_ctx);
+      if (rc != MAG_OK) { set_error(g_fwd.last_error()); delete w; return rc; }
+      *ctx_out = w;
+      return MAG_OK;
+    }
+  }
+#endif
   mag_ctx* c = new mag_ctx();
   c->P = *params;
   c->device = device;
@@ -279,6 +340,9 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
 
 void mag_destroy(mag_ctx_t* c) {
   if (!c) return;
+#if MAG_TEAM == 64
+  if (c->fwd_ctx) { g_fwd.destroy(c->fwd_ctx); delete c; return; }
+#endif
   cudaSetDevice(c->device);
   cudaFree(c->wsA); cudaFree(c->wsB); cudaFree(c->d_counter); cudaFree(c->d_arena_top); cudaFree(c->d_hist);
   cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena);
@@ -301,9 +365,13 @@ static int check_quantities(int32_t n_profile_q, const int32_t* profile_q, int32
 // 107; grid extensions reach ~330 in the example input but are rare); a batch that does not
 // fit is solved in several chunks, and a chunk that overflows the arena is reported as
 // MAG_ERR_CUDA with an explanatory message.
-#define ARENA_NX_BUDGET 176
 #define ARENA_ARRAYS (R_COUNT + CHAIN_JOB_ARRAYS + 1)   // record arrays + the arrays of a chain job (+ seeds of reseeded snapshots)
-static long long arena_need(int chunk, int nz) { return (long long)chunk * nz * ARENA_ARRAYS * ARENA_NX_BUDGET; }
+static long long arena_need(const mag_ctx* c, int chunk, int nz) {
+  // average points per snapshot budgeted: 1.65 x the default grid (176 for nx = 107; grid
+  // extensions reach 3 x nx in the example input but only for ~1 % of the snapshots)
+  const long long nx_budget = ((long long)(c->P.p_nx_ref + 2 * MAG_NGHOST) * 165 + 99) / 100;
+  return (long long)chunk * nz * ARENA_ARRAYS * nx_budget;
+}
 
 static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
   if (c->chunk_cap > 0 && nz <= c->nz_cap && (ngal <= c->chunk_cap)) { *chunk_out = ngal; return MAG_OK; }
@@ -314,7 +382,7 @@ static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
   const char* env = getenv("MAG_ARENA_FRACTION");
   const double frac = env ? atof(env) : 0.5;
   const size_t per_gal = (size_t)nz * (sizeof(SnapRec) + 2 * sizeof(ChainJob) + 2 * sizeof(int)) + sizeof(GalHead) + sizeof(int) +
-                         (size_t)arena_need(1, nz) * sizeof(double);
+                         (size_t)arena_need(c, 1, nz) * sizeof(double);
   long long chunk = (long long)((double)free_b * frac / (double)per_gal);
   if (chunk > ngal) chunk = ngal;
   if (chunk < 1) { set_error("not enough device memory for the snapshot records"); return MAG_ERR_CUDA; }
@@ -327,8 +395,8 @@ static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
   CUDA_TRY(cudaMalloc(&c->d_order, (size_t)chunk * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->d_recs, (size_t)chunk * nz * sizeof(SnapRec)));
   CUDA_TRY(cudaMalloc(&c->d_heads, (size_t)chunk * sizeof(GalHead)));
-  CUDA_TRY(cudaMalloc(&c->d_arena, (size_t)arena_need((int)chunk, nz) * sizeof(double)));
-  c->chunk_cap = (int)chunk; c->nz_cap = nz; c->arena_cap = arena_need((int)chunk, nz);
+  CUDA_TRY(cudaMalloc(&c->d_arena, (size_t)arena_need(c, (int)chunk, nz) * sizeof(double)));
+  c->chunk_cap = (int)chunk; c->nz_cap = nz; c->arena_cap = arena_need(c, (int)chunk, nz);
   *chunk_out = (int)chunk;
   return MAG_OK;
 }
@@ -401,6 +469,7 @@ static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int3
 int mag_solve_batch_device(mag_ctx_t* c, int32_t ngal, const int32_t* d_gal_ids, int32_t nz, const double* d_t_gyr,
                            const double* d_inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
                            const int32_t* scalar_q, const mag_outputs_t* d_out, void* cuda_stream) {
+  MAG_FWD(c, g_fwd.solve_dev(c->fwd_ctx, ngal, d_gal_ids, nz, d_t_gyr, d_inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, d_out, cuda_stream));
   if (!c || !d_out || ngal < 0) { set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT; }
   if (check_quantities(n_profile_q, profile_q, n_scalar_q, scalar_q)) { set_error("bad quantity id"); return MAG_ERR_BAD_ARGUMENT; }
   if (ngal == 0) return MAG_OK;
@@ -416,6 +485,13 @@ int mag_solve_batch_device(mag_ctx_t* c, int32_t ngal, const int32_t* d_gal_ids,
 int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t nz, const double* t_gyr,
                     const double* inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
                     const int32_t* scalar_q, const mag_outputs_t* out) {
+#if MAG_TEAM == 64
+  if (c && c->fwd_ctx) {
+    const int rc = g_fwd.solve(c->fwd_ctx, ngal, gal_ids, nz, t_gyr, inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, out);
+    if (rc != MAG_OK) set_error(g_fwd.last_error());
+    return rc;
+  }
+#endif
   if (!c || !out || ngal < 0 || !gal_ids || !t_gyr || !inputs) { set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT; }
   if (check_quantities(n_profile_q, profile_q, n_scalar_q, scalar_q)) { set_error("bad quantity id"); return MAG_ERR_BAD_ARGUMENT; }
   if (ngal == 0) return MAG_OK;
@@ -475,6 +551,7 @@ int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t 
 }
 
 int mag_last_timing(mag_ctx_t* c, double ms_out[4]) {
+  MAG_FWD(c, g_fwd.timing(c->fwd_ctx, ms_out));
   if (!c) return 0;
   float ms = 0;
   if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->last_ms[1] = ms;
@@ -484,6 +561,7 @@ int mag_last_timing(mag_ctx_t* c, double ms_out[4]) {
 }
 
 double mag_measure_fp64_peak(mag_ctx_t* c, int repeats) {
+  MAG_FWD(c, g_fwd.peak(c->fwd_ctx, repeats));
   if (!c) return 0.0;
   cudaSetDevice(c->device);
   const int threads = 256, blocks = c->sm_count * 8, iters = 1 << 14;
@@ -571,8 +649,10 @@ int mag_test_rng(int32_t igal, int32_t seed, int32_t kind, int32_t n, double* ou
   cudaFree(d);
   return MAG_OK;
 }
-int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nxcap, use_fast, replays of the last solve */) {
+int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nxcap, use_fast, replays of the last solve, ..., team */) {
+  MAG_FWD(c, g_fwd.info(c->fwd_ctx, out));
   if (!c) return MAG_ERR_BAD_ARGUMENT;
+  out[9] = MAG_TEAM;
   out[0] = c->sm_count; out[1] = c->ctasA_per_sm; out[2] = c->nwarpsA; out[3] = c->nxcap; out[4] = c->use_fast;
   out[5] = 0;
   cudaSetDevice(c->device);
@@ -581,6 +661,7 @@ int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nx
   return MAG_OK;
 }
 int mag_set_fast_path(mag_ctx_t* c, int32_t on) {
+  MAG_FWD(c, g_fwd.set_fast(c->fwd_ctx, on));
   if (!c) return MAG_ERR_BAD_ARGUMENT;
   c->use_fast = on ? 1 : 0;
   return MAG_OK;

@@ -221,3 +221,26 @@ def test_unstable_timestep_blow_up_and_retry_path(oracle, example_input):
     assert b"i" in ora["status"].tobytes() and (ora["flags"] & 4).any()   # the case really blows up
     compare(gpu, ora)
     assert replays > 0
+
+
+def test_fine_grid_config5(oracle, example_input):
+    """BASELINE config 5: 4x radial resolution (p_nx_ref = 401, nx = 407 and more after grid
+    extensions) with tightened Courant factors (0.045, passed as doubles as a namelist file
+    would).  Runs on 128-thread teams (4 points per thread); grids beyond 512 points fall
+    back to the generic path."""
+    from magnetizer_b200.solver import DynamoSolver
+    t, inputs = example_input
+    ids, sub = _subset(inputs, [1, 2, 60])
+    p = oracle.default_params()
+    p.p_nx_ref = 401
+    p.p_courant_v = 0.045
+    p.p_courant_eta = 0.045
+    s = DynamoSolver(params=p, device=0)
+    try:
+        gpu = s.run(ids, t, sub)
+        info = s.info()
+    finally:
+        s.close()
+    ora = oracle.solve_batch(p, ids, t, sub, nthreads=3)
+    rep = compare(gpu, ora)
+    print("config 5 worst errors:", {k: f"{v:.1e}" for k, v in rep.items() if v > 0}, info)
