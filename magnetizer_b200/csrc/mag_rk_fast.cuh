@@ -39,7 +39,7 @@ namespace magdev {
 // MAG_TEAM = 128 (libmagnetizer_b200_team128.so, for grids of more than 256 points, e.g.
 // p_nx_ref = 401 of BASELINE config 5); mag_create of the first forwards to the second.
 #ifndef MAG_TEAM
-#define MAG_TEAM 64
+#define MAG_TEAM 32
 #endif
 #define MAG_FAST_MAXPPL 8     // fast path up to nx = 512
 #define MAG_LINE_S (4 * MAG_TEAM + 8)   // shared line of the PPL <= 4 variants
@@ -75,7 +75,7 @@ struct RkShared {
   // (4 pad points each side, so that a thread's window -- own points +-3 -- is covered by
   // 16-byte aligned vector loads); for COEF_WSMEM the stencil weights [k][slot*64 + thread]
   // follow the short lines
-  alignas(16) double pool[2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM];
+  alignas(16) double pool[(2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM) > 1920 ? (2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM) : 1920];
 };
 static_assert(2 * 3 * MAG_LINE_L <= 2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM, "RkShared pool too small for the long lines");
 
@@ -139,7 +139,8 @@ __device__ __noinline__ void prepare_fast_coefs(Gal& G, int npts) {
 
 // ---- rigorous bound on the values check_f_error sees at the points the fast path does not
 // evaluate exactly: side 0 = the 3 inner ghost points and Br/Bp at the r = 0 point (their
-// stencils read points 0..6), side 1 = the 3 outer ghost points (points nx-7..nx-1)
+// stencils read points 0..6), side 1 = the 3 outer ghost points and Br/Bp at the outer
+// Dirichlet point nx-4, which the warp path does not evaluate exactly either (points nx-7..nx-1)
 __device__ __noinline__ void guard_constants(Gal& G, GuardK* out /* [2], shared memory */) {
   const int nx = G.nx;
   const double* x = G.A(A_X);
@@ -150,10 +151,10 @@ __device__ __noinline__ void guard_constants(Gal& G, GuardK* out /* [2], shared 
   const double Rk = fabs(G.a->P.R_kappa);
   for (int side = 0; side < 2; side++) {
     GuardK k = {0, 0, 0, 0, 0, 0, 0, 0};
-    // side 0: lanes 0-2 inner ghosts, lane 3 the centre; side 1: lanes 0-2 outer ghosts
-    const bool active = side == 0 ? G.lane < 4 : G.lane < 3;
+    // side 0: lanes 0-2 inner ghosts, lane 3 the centre; side 1: lane 0 the outer Dirichlet point, lanes 1-3 outer ghosts
+    const bool active = G.lane < 4;
     if (active) {
-      const int g = side == 0 ? G.lane : nx - 3 + G.lane;
+      const int g = side == 0 ? G.lane : nx - 4 + G.lane;
       const double ir = fabs(cIR[g]), cr = fabs(cCR[g]);
       if (!(side == 0 && G.lane == 3)) {
         k.kb_lin = fabs(cC1[g]) + cr * (ir * ir + S1 * ir + S2) + fabs(Gc[g]);
@@ -591,6 +592,12 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
   __syncthreads();
 }
 
+}  // namespace magdev
+#if MAG_TEAM == 32
+#include "mag_rk_warp.cuh"
+#endif
+namespace magdev {
+
 __device__ __forceinline__ void fast_dispatch(Gal* G, RkShared* rs) {
   switch (rs->call.ppl) {
     case 2: fast_loop_team<2, COEF_REGS>(G, rs); break;
@@ -604,6 +611,9 @@ __device__ __forceinline__ void fast_dispatch(Gal* G, RkShared* rs) {
 // field blew up, check_f_error).
 __device__ bool run_timesteps(Gal& G, RkShared* rs) {
   if (G.nsteps < 1) return true;
+#if MAG_TEAM == 32
+  if (G.a->use_fast && warp_path_applies(G)) return warp_dispatch(G, rs);
+#endif
   if (G.a->use_fast && G.nx >= 32 && G.nx <= MAG_FAST_MAXPPL * MAG_TEAM) {
     if (G.lane == 0) {
       FastCall& C = rs->call;

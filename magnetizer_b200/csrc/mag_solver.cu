@@ -25,7 +25,11 @@ using namespace magdev;
 #define MAG_PROFILE_MAXREG 128   // 16 warps per SM: the profile phase is latency bound (serial root-finder chains)
 #endif
 #ifndef MAG_EVOLVE_MAXREG
-#define MAG_EVOLVE_MAXREG 168   // 6 teams of 64 threads per SM
+#if MAG_TEAM == 32
+#define MAG_EVOLVE_MAXREG 255   // 8 one-warp teams per SM, everything of a galaxy in registers
+#else
+#define MAG_EVOLVE_MAXREG 168
+#endif
 #endif
 
 static thread_local std::string g_last_error;
@@ -190,7 +194,7 @@ struct mag_ctx {
   mag_ctx* fwd_ctx = nullptr;
 };
 
-#if MAG_TEAM == 64
+#if MAG_TEAM == 32
 namespace {
 struct FwdApi {
   int (*create)(const mag_params_t*, int, mag_ctx_t**);
@@ -286,8 +290,8 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) { set_error("kernels are built for sm_100a only"); return MAG_ERR_NO_DEVICE; }
-#if MAG_TEAM == 64
-  if (params->p_nx_ref + 2 * MAG_NGHOST > 4 * MAG_TEAM) {
+#if MAG_TEAM == 32
+  if (params->p_nx_ref + 2 * MAG_NGHOST > 256) {
     // more than 256 grid points: use the 128-thread-team build if it is there (same ABI)
     if (void* h = open_big_team_library()) {
       mag_ctx* w = new mag_ctx();
@@ -321,6 +325,9 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   if (cap > params->p_nx_MAX) cap = params->p_nx_MAX;
   if (cap < params->p_nx_ref + 6) cap = params->p_nx_ref + 6;
   if (cap < MAG_FAST_MAXPPL * MAG_TEAM) cap = MAG_FAST_MAXPPL * MAG_TEAM;  // the fast path addresses up to 256 points
+#if MAG_TEAM == 32
+  if (cap < 1024) cap = 1024;   // room for the coefficient pair table of the large-grid warp variants (mag_rk_warp.cuh)
+#endif
   c->nxcap = (cap + 15) & ~15;
   const size_t wsA = (size_t)c->nwarpsA * A_COUNT * c->nxcap * sizeof(double);
   const size_t wsB = (size_t)c->nteamsB * A_COUNT * c->nxcap * sizeof(double);
@@ -340,7 +347,7 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
 
 void mag_destroy(mag_ctx_t* c) {
   if (!c) return;
-#if MAG_TEAM == 64
+#if MAG_TEAM == 32
   if (c->fwd_ctx) { g_fwd.destroy(c->fwd_ctx); delete c; return; }
 #endif
   cudaSetDevice(c->device);
@@ -485,7 +492,7 @@ int mag_solve_batch_device(mag_ctx_t* c, int32_t ngal, const int32_t* d_gal_ids,
 int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t nz, const double* t_gyr,
                     const double* inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
                     const int32_t* scalar_q, const mag_outputs_t* out) {
-#if MAG_TEAM == 64
+#if MAG_TEAM == 32
   if (c && c->fwd_ctx) {
     const int rc = g_fwd.solve(c->fwd_ctx, ngal, gal_ids, nz, t_gyr, inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, out);
     if (rc != MAG_OK) set_error(g_fwd.last_error());
