@@ -19,6 +19,17 @@
 
 namespace magdev {
 
+// optional phase clocks (debug builds, -DMAG_PHASE_CLOCKS): cycles lane 0 of every evolve team
+// spends in each phase of a snapshot, summed over the launch
+#ifdef MAG_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define PHASE_BEGIN long long _pc0 = clock64()
+#define PHASE_END(id, lane) do { const long long _pc1 = clock64(); if ((lane) == 0) atomicAdd(&g_phase_clk[id], (unsigned long long)(_pc1 - _pc0)); _pc0 = _pc1; } while (0)
+#else
+#define PHASE_BEGIN do {} while (0)
+#define PHASE_END(id, lane) do {} while (0)
+#endif
+
 struct SnapRec;
 struct GalHead;
 struct ChainJob;

@@ -322,6 +322,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
     const SnapRec R = recs[it - 1];
     if (!(R.flags & SR_VALID)) break;
     bool ok = true;
+    PHASE_BEGIN;
     if (R.flags & SR_TRAP) {
       for (int v = 0; v < 3; v++) { double* f = G.A(A_F0 + v); for (int i = lane; i < G.nx; i += 32) f[i] = 0.0; }
       __syncwarp();
@@ -357,6 +358,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
       }
       __syncwarp();
     }
+    PHASE_END(0, lane);
     for (int fail_count = 0; fail_count <= P.p_MAX_FAILS; fail_count++) {
       ok = true;
       if (!(R.flags & SR_SOLVE)) {
@@ -377,6 +379,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
       }
       __syncwarp();
     }
+    PHASE_END(1, lane);
     bool last = (R.flags & SR_LAST) != 0;
     if (!ok) {
       G.status = 'i';
@@ -387,6 +390,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
     impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
     estimate_Bzmod(G);
     write_field_rows(G, it);
+    PHASE_END(2, lane);
     if (last) break;
   }
   if (lane == 0) {

@@ -3,13 +3,17 @@
 //
 // Layout.  The live points of the grid are g = 3 .. m (m = nx-4; gutsdynamo.f90:55-86:
 // g = 3 and g = m are the Dirichlet points of Br, Bp; g < 3 and g > m are ghost zones).
-// With p = g - 3 in [0, P] (P = nx-7), slot s = p + J0 belongs to lane s / PPL, register
-// j = s % PPL.  J0 = PPL-1 - P % PPL puts the LAST live point into the last register of its
-// lane (lane tm), so the outer ghost zone is exactly that lane's right halo; the inner ghost
-// zone is the J0 leading registers of lane 0 plus its left halo.  Ghost values are never
-// stored: after the shuffles the three lanes that see a ghost point (0, 1 and tm) overwrite
-// those window entries with the mirror image (negated for Br, Bp) of entries they already
-// hold -- a handful of predicated register moves with compile-time indices.
+// With p = g - 3 in [0, P] (P = nx-7), slot s = p + 2 belongs to lane s / PPL, register
+// j = s % PPL: the inner end is fixed (p = 0 in register 2 of lane 0), the outer end falls
+// on register jm = (P+2) % PPL of lane tm = (P+2) / PPL, a run-time position that only two
+// small warp-uniform switches per stage look at.  The loop is therefore instantiated once
+// per PPL and not once per alignment: all the warps of an SM that work on grids of the same
+// size class share one loop body in the instruction caches (with one instantiation per
+// alignment, ncu showed 15 stall_no_instruction cycles per issue on the mixed catalogue).
+// Ghost values are never stored.  Slots outside the live range are inert (all coefficients
+// zero, value 0), which is exactly what Br and Bp need once the boundary conditions are folded
+// into the stencil weights (fold_boundary_weights); the four alp_m ghost entries that keep a
+// non-zero weight are copied inside the window of the lane that uses them.
 //
 // Per stage and thread: 36 SHFL (3 variables x 6 halo values x 2 words), then for each of the
 // PPL points the folded right-hand side of mag_rk_fast.cuh with two more foldings
@@ -36,6 +40,16 @@ namespace magdev {
 // the global table adds q = 4..7: (ca,gs) (c0,fk) (ak,p3) (qc,-).
 // The loads are volatile asm so that the compiler cannot hoist them out of the time loop (the
 // table is loop invariant; hoisting would put it back into registers and spill).
+// Up to which PPL the three stages of a step are unrolled.  Unrolled loops are ~40 % faster
+// when every warp of an SM runs the same variant, but eight warps running eight different
+// 15-20 KB loops thrash the instruction caches (ncu: stall_no_instruction 15 cycles per
+// issue on the synthetic catalogue), so the default is the looped body.
+#ifndef MAG_WARP_SPECIALIZE_DEFAULT
+#define MAG_WARP_SPECIALIZE_DEFAULT 0
+#endif
+#ifndef MAG_WARP_UNROLL_MAXPPL
+#define MAG_WARP_UNROLL_MAXPPL 0
+#endif
 #define WM_REGS 0
 #define WM_WSM 1
 #define WM_WSM2 2
@@ -58,6 +72,7 @@ __device__ __forceinline__ double2 ldg_pair(const double2* p) {
 template <int PPL, int MODE>
 struct WarpState {
   double f[3][PPL], ft[3][PPL];
+  double hl[3][3], hr[3][3];   // halo: the last 3 registers of lane-1, the first 3 of lane+1 (filled by warp_exchange)
   double w[MODE == WM_REGS ? PPL : 1][8];
   double ca[MODE == WM_ALLG ? 1 : PPL], gs[MODE == WM_ALLG ? 1 : PPL], c0[MODE == WM_ALLG ? 1 : PPL];
   double fk[MODE == WM_ALLG ? 1 : PPL], ak[MODE == WM_ALLG ? 1 : PPL];
@@ -66,15 +81,19 @@ struct WarpState {
 
 // ---- boundary conditions folded into the stencil weights.  With ghost value = sigma * mirror
 // value (sigma = -1 for Br, Bp; +1 for alp_m) the weight of a ghost offset o of a point at
-// distance d from the Dirichlet point moves onto its mirror offset o' = -2d - o:
-//   d = 0 (Dirichlet point; only alp_m evolves there): w[o'] += w[o], w[o] = 0
+// distance d from the Dirichlet point meets its mirror offset o' = -2d - o:
+//   d = 0 (the Dirichlet point itself): w[o] += w[o'], w[o'] = 0 -- the whole weight sits on the
+//          ghost side, where Br and Bp read zeros: with ca = gs = c0 = fk = 0 at that point
+//          Br = Bp = 0 is then preserved exactly without ever resetting it, while alp_m, whose
+//          ghost entries hold the mirror values, sees w[o] + w[o'];
 //   o' = 0 (the mirror is the point itself): centre weight of B -= w[o], centre weight of
-//          alp_m += R_kappa*w[o], w[o] = 0
-//   else: w[o'] -= w[o] (exact for Br, Bp if their ghost entry reads 0) and w[o] *= 2, so that
-//          alp_m, whose ghost entry holds the mirror value, sees w[o'] + w[o].
-// Only four ghost entries keep a non-zero weight: p = -2, -1 (used by p = 1, 2) and P+1, P+2
-// (used by P-2, P-1).  The values Br, Bp take AT the Dirichlet points before impose_bc resets
-// them are not evaluated exactly any more; guard_constants bounds them with the ghost points.
+//          alp_m += R_kappa*w[o], w[o] = 0;
+//   else: w[o'] -= w[o] (exact for Br, Bp, ghost entry 0) and w[o] *= 2, so that alp_m sees
+//          w[o'] + w[o].
+// The only boundary work left in a stage is to copy three alp_m values per end into the
+// ghost entries of the window (mirror image about the Dirichlet point).  The values Br, Bp
+// take AT the Dirichlet points before impose_bc resets them in the reference are not
+// evaluated; guard_constants bounds them together with the ghost points.
 __device__ __noinline__ void fold_boundary_weights(Gal& G) {
   const int nx = G.nx, m = nx - MAG_NGHOST - 1;
   const double Rk = G.a->P.R_kappa;
@@ -88,7 +107,7 @@ __device__ __noinline__ void fold_boundary_weights(Gal& G) {
       for (int o = -3; o < -d; o++) {          // ghost offsets (inward positive)
         const int io = left ? 3 + o : 3 - o;
         const int om = -2 * d - o, im = left ? 3 + om : 3 - om;
-        if (d == 0) { w[im] += w[io]; w[io] = 0.0; }
+        if (d == 0) { w[io] += w[im]; w[im] = 0.0; }
         else if (om == 0) { wc -= w[io]; w0a += Rk * w[io]; w[io] = 0.0; }
         else { w[im] -= w[io]; w[io] *= 2.0; }
       }
@@ -100,33 +119,88 @@ __device__ __noinline__ void fold_boundary_weights(Gal& G) {
   __syncwarp();
 }
 
-// One Runge-Kutta stage.  STAGE: 0,1,2.  R_kappa = 1 (folded into the alp_m chain).
-template <int PPL, int J0, int MODE, int STAGE>
-__device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsigned wsa, const double2* __restrict__ tab, const int lane,
-                                           const int tm, const double dg, const double dz, unsigned& mBs, unsigned& mBu,
-                                           unsigned& mAs, unsigned& mAu, double* __restrict__ alp_out, const int g0, const int m) {
-  // lanes / window indices of the four alp_m ghost entries with a non-zero weight
-  constexpr int L1 = (J0 + 1) / PPL, I1 = 3 + J0 - 2 - PPL * L1, S1 = 3 + J0 + 2 - PPL * L1;   // p = -2 <- p = 2, for p = 1
-  constexpr int L2 = (J0 + 2) / PPL, I2 = 3 + J0 - 1 - PPL * L2, S2 = 3 + J0 + 1 - PPL * L2;   // p = -1 <- p = 1, for p = 2
-  constexpr int LD = J0 / PPL, JD = J0 % PPL;                                                // inner Dirichlet point
-  static_assert(I1 >= 0 && I2 >= 0 && S1 <= PPL + 5 && S2 <= PPL + 5 && J0 >= 2 && J0 <= PPL + 1, "warp_stage layout");
-  const bool isM = lane == tm;
-  // ---- windows: own registers + 3 halo values each side
-  double win[3][PPL + 6];
+// One Runge-Kutta stage; R_kappa = 1 (folded into the alp_m chain).  The same code serves the
+// three stages: ftmp == f holds at the start of every step, so stage 1 can read its base from
+// ftmp like the others, and stage 3 re-establishes it (LAST, or dz = 0: fma(0, p, n) = n).
+// Window entry i of alp_m (i = 0..2: left halo, 3..PPL+2: own registers, PPL+3..PPL+5: right halo)
+template <int PPL, int MODE>
+__device__ __forceinline__ double& wref(WarpState<PPL, MODE>& S, const int i) {
+  return i < 3 ? S.hl[2][i < 3 ? i : 0] : (i < PPL + 3 ? S.f[2][(i >= 3 && i < PPL + 3) ? i - 3 : 0] : S.hr[2][i >= PPL + 3 ? i - PPL - 3 : 0]);
+}
+// mirror image of alp_m about a Dirichlet point that sits at window entry IP of lane `owner`
+template <int PPL, int MODE, int IP>
+__device__ __forceinline__ void mirror_ghosts(WarpState<PPL, MODE>& S, const bool mine, const bool outward_up) {
+#pragma unroll
+  for (int k = 1; k <= 3; k++) {
+    const int dst = outward_up ? IP + k : IP - k, src = outward_up ? IP - k : IP + k;
+    if (dst >= 0 && dst <= PPL + 5 && src >= 0 && src <= PPL + 5) {
+      const double v = wref<PPL, MODE>(S, src);
+      if (mine) wref<PPL, MODE>(S, dst) = v;
+    }
+  }
+}
+template <int PPL, int MODE, int JMC>
+__device__ __forceinline__ void outer_ghosts(WarpState<PPL, MODE>& S, const int lane, const int tm) {
+  mirror_ghosts<PPL, MODE, 3 + JMC>(S, lane == tm, true);
+  if (JMC <= 1) mirror_ghosts<PPL, MODE, PPL + 3 + JMC>(S, lane == tm - 1, true);
+}
+
+// Halo exchange after a stage (or after loading the state): 36 SHFL, then the Neumann ghost
+// entries of alp_m.  Br and Bp need nothing: their ghost entries are inert registers that read
+// 0.  JM >= 0: the outer Dirichlet point sits in register JM of lane tm (compile time);
+// JM = -1: in register jm (one warp-uniform switch).  The inner one, p = 0, sits in register
+// WARP_J0 = 3 of lane 0, so that p = -3..-1 are its (inert) registers 0..2.
+#define WARP_J0 3
+template <int PPL, int MODE, int JM>
+__device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int lane, const int tm, const int jm) {
 #pragma unroll
   for (int v = 0; v < 3; v++) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      win[v][k] = __shfl_up_sync(FULL, S.f[v][PPL - 3 + k], 1);
-      win[v][PPL + 3 + k] = __shfl_down_sync(FULL, S.f[v][k], 1);
+      S.hr[v][k] = __shfl_down_sync(FULL, S.f[v][k], 1);
+      S.hl[v][k] = __shfl_up_sync(FULL, S.f[v][PPL - 3 + k], 1);
     }
+  }
+  // inner end: the ghost entries of p = 0 (all three), of p = 1 (p = -2) and of p = 2 (p = -1)
+  // live in the windows of the lanes that own those points
+  constexpr int J0 = WARP_J0;
+  constexpr int LA = J0 / PPL, LB = (J0 + 1) / PPL, LC = (J0 + 2) / PPL;
+  mirror_ghosts<PPL, MODE, 3 + J0 - PPL * LA>(S, lane == LA, false);
+  if (LB != LA) mirror_ghosts<PPL, MODE, 3 + J0 - PPL * LB>(S, lane == LB, false);
+  if (LC != LB) mirror_ghosts<PPL, MODE, 3 + J0 - PPL * LC>(S, lane == LC, false);
+  // outer end
+  if (JM >= 0) {
+    outer_ghosts<PPL, MODE, (JM >= 0 ? JM : 0)>(S, lane, tm);
+  } else {
+    switch (jm) {
+      case 0: outer_ghosts<PPL, MODE, 0>(S, lane, tm); break;
+      case 1: outer_ghosts<PPL, MODE, 1>(S, lane, tm); break;
+      case 2: outer_ghosts<PPL, MODE, 2>(S, lane, tm); break;
+      case 3: outer_ghosts<PPL, MODE, 3>(S, lane, tm); break;
+      case 4: if (PPL > 4) outer_ghosts<PPL, MODE, (PPL > 4 ? 4 : 0)>(S, lane, tm); break;
+      case 5: if (PPL > 5) outer_ghosts<PPL, MODE, (PPL > 5 ? 5 : 0)>(S, lane, tm); break;
+      case 6: if (PPL > 6) outer_ghosts<PPL, MODE, (PPL > 6 ? 6 : 0)>(S, lane, tm); break;
+      case 7: if (PPL > 7) outer_ghosts<PPL, MODE, (PPL > 7 ? 7 : 0)>(S, lane, tm); break;
+      case 8: if (PPL > 8) outer_ghosts<PPL, MODE, (PPL > 8 ? 8 : 0)>(S, lane, tm); break;
+      case 9: if (PPL > 9) outer_ghosts<PPL, MODE, (PPL > 9 ? 9 : 0)>(S, lane, tm); break;
+      default: if (PPL > 10) outer_ghosts<PPL, MODE, (PPL > 10 ? 10 : 0)>(S, lane, tm); break;
+    }
+  }
+}
+
+// One Runge-Kutta stage on the window (hl, f, hr) that warp_exchange left behind.
+template <int PPL, int MODE, bool LAST>
+__device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsigned wsa, const double2* __restrict__ tab, const int lane,
+                                           const double dg, const double dz, unsigned& mBs, unsigned& mBu,
+                                           unsigned& mAs, unsigned& mAu, double* __restrict__ alp_out, const int g0, const int m) {
+  double win[3][PPL + 6];
+#pragma unroll
+  for (int v = 0; v < 3; v++) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { win[v][k] = S.hl[v][k]; win[v][PPL + 3 + k] = S.hr[v][k]; }
 #pragma unroll
     for (int j = 0; j < PPL; j++) win[v][3 + j] = S.f[v][j];
   }
-  // Neumann ghost entries of alp_m (Br, Bp read the zeros of the inert slots)
-  if (lane == L1) win[2][I1] = win[2][S1];
-  if (lane == L2) win[2][I2] = win[2][S2];
-  if (isM) { win[2][PPL + 3] = win[2][PPL + 1]; win[2][PPL + 4] = win[2][PPL]; }
   // ---- point by point: three stencil chains, point-wise terms, Runge-Kutta update
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
@@ -170,42 +244,40 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
     const double B2 = fma(Br, Br, Bp * Bp);
     const double em = fma(c_qc * fast_sqrt_abs(a), Br * Bp, a * B2);
     const double p2 = fma(c_p3, em, a2);
-    const double b0 = (STAGE == 0) ? Br : S.ft[0][j];
-    const double b1 = (STAGE == 0) ? Bp : S.ft[1][j];
-    const double b2 = (STAGE == 0) ? am : S.ft[2][j];
-    const double n0 = fma(dg, p0, b0), n1 = fma(dg, p1, b1), n2 = fma(dg, p2, b2);
+    const double n0 = fma(dg, p0, S.ft[0][j]), n1 = fma(dg, p1, S.ft[1][j]), n2 = fma(dg, p2, S.ft[2][j]);
     S.f[0][j] = n0; S.f[1][j] = n1; S.f[2][j] = n2;
-    if (STAGE < 2) { S.ft[0][j] = fma(dz, p0, n0); S.ft[1][j] = fma(dz, p1, n1); S.ft[2][j] = fma(dz, p2, n2); }
+    if (LAST) { S.ft[0][j] = n0; S.ft[1][j] = n1; S.ft[2][j] = n2; }
+    else { S.ft[0][j] = fma(dz, p0, n0); S.ft[1][j] = fma(dz, p1, n1); S.ft[2][j] = fma(dz, p2, n2); }
     // |x| maxima on the high words: signed max catches the positive values, unsigned max the negative ones
     mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(n0), __double2hiint(n1));
     mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(n0), (unsigned)__double2hiint(n1));
     mAs = (unsigned)max((int)mAs, __double2hiint(n2));
     mAu = max(mAu, (unsigned)__double2hiint(n2));
   }
-  // ---- Dirichlet points of Br, Bp: the state the next pde call sees is 0 (ftmp keeps the
-  // unreset value, like the reference's ftmp)
-  if (lane == LD) { S.f[0][JD] = 0.0; S.f[1][JD] = 0.0; }
-  if (isM) { S.f[0][PPL - 1] = 0.0; S.f[1][PPL - 1] = 0.0; }
 }
 
 // Fast time loop of one snapshot attempt on one warp.  Returns ok (false: check_f_error).
-template <int PPL, int J0, int MODE>
+template <int PPL, int MODE, int JM>
 __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
   const int lane = G.lane;
   double* const W = G.W;
   const int nxcap = G.a->nxcap, nx = G.nx, m = nx - MAG_NGHOST - 1, nsteps = G.nsteps;
   const int P = nx - 2 * MAG_NGHOST - 1;
-  const int tm = (P + J0) / PPL;
+  const int tm = (P + WARP_J0) / PPL, jm = (P + WARP_J0) % PPL;
   const double dt = G.dt;
   auto WA = [&](int id) { return W + (size_t)id * nxcap; };
-  const int g0 = lane * PPL - J0 + MAG_NGHOST;   // grid index of register 0
+  const int g0 = lane * PPL - WARP_J0 + MAG_NGHOST;   // grid index of register 0 (slot s holds p = s - WARP_J0, g = p + 3)
   double2* const wt2 = reinterpret_cast<double2*>(rs->pool) + lane;                          // shared pair table, this lane's column
   double2* const tab = reinterpret_cast<double2*>(W + (size_t)WARP_TABLE_ARRAY * nxcap) + lane;   // global pair table
   const unsigned wsa = (unsigned)__cvta_generic_to_shared(rs->pool) + 16u * lane;
 
+  PHASE_BEGIN;
   prepare_fast_coefs(G, nx);
+  PHASE_END(3, lane);
   guard_constants(G, rs->gk);
+  PHASE_END(4, lane);
   fold_boundary_weights(G);
+  PHASE_END(5, lane);
 
   WarpState<PPL, MODE> S;
 #pragma unroll
@@ -216,7 +288,8 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
     double w[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) w[k] = live ? WA(C_W0 + k)[gc] : 0.0;   // C_W0..C_W6, C_W0A are consecutive
-    const double ca = live ? WA(F_CA)[gc] : 0.0, gs = live ? WA(F_GS)[gc] : 0.0, ak = live ? WA(F_AK)[gc] : 0.0;
+    const bool bfree = live && g != MAG_NGHOST && g != m;   // Br, Bp evolve here (not a Dirichlet point)
+    const double ca = bfree ? WA(F_CA)[gc] : 0.0, gs = bfree ? WA(F_GS)[gc] : 0.0, ak = live ? WA(F_AK)[gc] : 0.0;
     const double p3 = live ? WA(F_P3)[gc] : 0.0, qc = live ? WA(F_QC)[gc] : 0.0;
     if (MODE == WM_REGS) {
 #pragma unroll
@@ -242,7 +315,7 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
       const int g = g0 + j;
       const bool live = g >= MAG_NGHOST && g <= m;
       const int gc = live ? g : 0;
-      const double fb = live ? sg[gc] * cFB[gc] : 0.0;
+      const double fb = (live && g != MAG_NGHOST && g != m) ? sg[gc] * cFB[gc] : 0.0;
       const double fk = live ? fb * kd[gc] : 0.0;
       const double c0 = fma(fk, live ? akp[gc] : 0.0, fb);
       if (MODE == WM_ALLG) tab[GSLOT2(j, 5)] = make_double2(c0, fk);
@@ -258,14 +331,18 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
       const bool live = g >= MAG_NGHOST && g <= m;
       const int gc = live ? g : 0;
 #pragma unroll
-      for (int v = 0; v < 3; v++) { S.f[v][j] = live ? WA(A_F0 + v)[gc] : 0.0; S.ft[v][j] = 0.0; }
+      for (int v = 0; v < 3; v++) S.f[v][j] = (live && (v == 2 || (g != MAG_NGHOST && g != m))) ? WA(A_F0 + v)[gc] : 0.0;
     }
-    if (lane == J0 / PPL) { S.f[0][J0 % PPL] = 0.0; S.f[1][J0 % PPL] = 0.0; }
-    if (lane == tm) { S.f[0][PPL - 1] = 0.0; S.f[1][PPL - 1] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < PPL; j++)
+#pragma unroll
+      for (int v = 0; v < 3; v++) S.ft[v][j] = S.f[v][j];
+    warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
   };
   load_signed_floor();
   load_state();
   __syncwarp();
+  PHASE_END(6, lane);
 
   const double dg0 = dt * (8.0 / 15), dg1 = dt * (5.0 / 12), dg2 = dt * (3.0 / 4);
   const double dz0 = dt * (-17.0 / 60), dz1 = dt * (-5.0 / 12);
@@ -306,6 +383,9 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
       // or if the grid size changed (floor_field.f90:55-79)
       const bool due = this_t - t_last > tmk;
       if (due || refresh || sign_nx != nx) {
+#ifdef MAG_PHASE_CLOCKS
+        const long long _r0 = clock64();
+#endif
         if (!signs_saved) {  // first refresh of the block: keep the old signs for a replay
           const double* sg = WA(A_SIGN); double* bk = WA(A_OMK);
           const int nsave = max(nx, ck_sign_nx);
@@ -318,22 +398,38 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
         if (due) t_last = this_t;
         refresh = false; sign_nx = nx;
         load_signed_floor();
+#ifdef MAG_PHASE_CLOCKS
+        if (lane == 0) { atomicAdd(&g_phase_clk[8], (unsigned long long)(clock64() - _r0)); atomicAdd(&g_phase_clk[9], 1ull); }
+#endif
       }
       double* alp_out = (jt + s == nsteps) ? WA(A_ALP) : nullptr;
-      warp_stage<PPL, J0, MODE, 0>(S, wsa, tab, lane, tm, dg0, dz0, mBs, mBu, mAs, mAu, nullptr, g0, m);
-      warp_stage<PPL, J0, MODE, 1>(S, wsa, tab, lane, tm, dg1, dz1, mBs, mBu, mAs, mAu, nullptr, g0, m);
-      warp_stage<PPL, J0, MODE, 2>(S, wsa, tab, lane, tm, dg2, 0.0, mBs, mBu, mAs, mAu, alp_out, g0, m);
+      if (JM >= 0 || PPL <= MAG_WARP_UNROLL_MAXPPL) {  // three stages unrolled: their shuffles and chains overlap
+        warp_stage<PPL, MODE, false>(S, wsa, tab, lane, dg0, dz0, mBs, mBu, mAs, mAu, nullptr, g0, m);
+        warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+        warp_stage<PPL, MODE, false>(S, wsa, tab, lane, dg1, dz1, mBs, mBu, mAs, mAu, nullptr, g0, m);
+        warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+        warp_stage<PPL, MODE, true>(S, wsa, tab, lane, dg2, 0.0, mBs, mBu, mAs, mAu, alp_out, g0, m);
+        warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+      } else {         // one stage body, looped: a three times smaller instruction footprint
+#pragma unroll 1
+        for (int st = 0; st < 3; st++) {
+          const double dg = st == 0 ? dg0 : (st == 1 ? dg1 : dg2), dz = st == 0 ? dz0 : (st == 1 ? dz1 : 0.0);
+          warp_stage<PPL, MODE, false>(S, wsa, tab, lane, dg, dz, mBs, mBu, mAs, mAu, st == 2 ? alp_out : nullptr, g0, m);
+          warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+        }
+      }
       // t = t + dt*gam1 ; ttmp = t + dt*zet1 ; t = ttmp + dt*gam2 ; ttmp = t + dt*zet2 ; t = ttmp + dt*gam3
       double tt = t + dg0;
       tt = tt + dz0; tt = tt + dg1; tt = tt + dz1; tt = tt + dg2;
       t = tt;
     }
-    // ---- accept or replay the block.  Per-lane maxima of lanes 0,1 / tm bound the 7 points
+    // ---- accept or replay the block.  Per-lane maxima of lanes 0,1 / tm-1,tm bound the 7 points
     // next to the inner / outer boundary (a superset of them: conservative).
     const unsigned mB = max(mBs, mBu & 0x7fffffffu), mA = max(mAs, mAu & 0x7fffffffu);
     const unsigned nB0 = max(__shfl_sync(FULL, mB, 0), __shfl_sync(FULL, mB, 1));
     const unsigned nA0 = max(__shfl_sync(FULL, mA, 0), __shfl_sync(FULL, mA, 1));
-    const unsigned nB1 = __shfl_sync(FULL, mB, tm), nA1 = __shfl_sync(FULL, mA, tm);
+    const unsigned nB1 = max(__shfl_sync(FULL, mB, tm), __shfl_sync(FULL, mB, tm - 1));
+    const unsigned nA1 = max(__shfl_sync(FULL, mA, tm), __shfl_sync(FULL, mA, tm - 1));
     unsigned rB = mB, rA = mA;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -388,52 +484,39 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
   G.t = t; G.t_last_sign_choice = t_last; G.refresh_sign = refresh; G.sign_nx = sign_nx;
   G.point_stages += stages;
   __syncwarp();
+  PHASE_END(7, lane);
+#ifdef MAG_PHASE_CLOCKS
+  if (lane == 0) { atomicAdd(&g_phase_clk[10], 1ull); atomicAdd(&g_phase_clk[11], (unsigned long long)nsteps); }
+#endif
   return ok;
 }
 
-// Layout of a grid of nx points: registers per lane and the offset J0 in [2, PPL+1] that puts the
-// last live point into the last register of a lane <= 30 (lane 31 must stay inert: it feeds
-// the zeros of the outer ghost zone); ppl = 0 if the warp path does not take this grid.
-__device__ __forceinline__ void warp_layout(int nx, int& ppl, int& j0) {
+// Registers per lane for a grid of nx points: the two outer alp_m ghost entries must still
+// fall into a lane (slots up to P+4 < 32*PPL); 0 if the warp path does not take this grid.
+__device__ __forceinline__ int warp_ppl(int nx) {
   const int P = nx - 2 * MAG_NGHOST - 1;
   const int cand[5] = {4, 5, 6, 8, 11};
-  for (int c = 0; c < 5; c++) {
-    ppl = cand[c];
-    j0 = ppl - 1 - P % ppl;
-    if (j0 < 2) j0 += ppl;
-    if ((P + j0) / ppl <= 30) return;
-  }
-  ppl = 0;
+  for (int c = 0; c < 5; c++)
+    if (P + WARP_J0 + 3 < 32 * cand[c]) return cand[c];
+  return 0;
 }
 // (R_kappa = 1, the reference's default, is folded into the alp_m stencil chain; other values
 // take the shared-line path of mag_rk_fast.cuh)
 __device__ __forceinline__ bool warp_path_applies(const Gal& G) {
-  int ppl, j0;
-  warp_layout(G.nx, ppl, j0);
+  const int ppl = warp_ppl(G.nx);
   if (ppl >= 8 && (size_t)WARP_TABLE_ARRAYS * G.a->nxcap < (size_t)16 * 32 * ppl) return false;   // pair table does not fit
   return G.a->P.R_kappa == 1.0 && G.nx >= 64 && ppl != 0;
 }
-
-template <int PPL, int MODE, int J>
-struct WarpJ0 {
-  static __device__ __forceinline__ bool run(Gal& G, RkShared* rs, int j0) {
-    if (j0 == J) return warp_loop<PPL, J, MODE>(G, rs);
-    return WarpJ0<PPL, MODE, J + 1>::run(G, rs, j0);
-  }
-};
-template <int PPL, int MODE>
-struct WarpJ0<PPL, MODE, PPL + 2> {
-  static __device__ __forceinline__ bool run(Gal&, RkShared*, int) { return false; }
-};
 __device__ __forceinline__ bool warp_dispatch(Gal& G, RkShared* rs) {
-  int ppl, j0;
-  warp_layout(G.nx, ppl, j0);
-  switch (ppl) {
-    case 4: return WarpJ0<4, WM_REGS, 2>::run(G, rs, j0);
-    case 5: return WarpJ0<5, WM_WSM, 2>::run(G, rs, j0);
-    case 6: return WarpJ0<6, WM_WSM2, 2>::run(G, rs, j0);
-    case 8: return WarpJ0<8, WM_ALLG, 2>::run(G, rs, j0);
-    default: return WarpJ0<11, WM_ALLG, 2>::run(G, rs, j0);
+  // the default grid (p_nx_ref = 101: nx = 107, most of the work) has its own instantiation with
+  // a compile-time outer alignment and the three stages unrolled
+  if (MAG_WARP_SPECIALIZE_DEFAULT && G.nx == 107) return warp_loop<4, WM_REGS, 3>(G, rs);
+  switch (warp_ppl(G.nx)) {
+    case 4: return warp_loop<4, WM_REGS, -1>(G, rs);
+    case 5: return warp_loop<5, WM_WSM, -1>(G, rs);
+    case 6: return warp_loop<6, WM_WSM2, -1>(G, rs);
+    case 8: return warp_loop<8, WM_ALLG, -1>(G, rs);
+    default: return warp_loop<11, WM_ALLG, -1>(G, rs);
   }
 }
 

@@ -675,3 +675,11 @@ int mag_set_fast_path(mag_ctx_t* c, int32_t on) {
 }
 
 }  // extern "C"
+
+#ifdef MAG_PHASE_CLOCKS
+extern "C" int mag_debug_phase_clocks(unsigned long long* out, int reset) {
+  if (out && cudaMemcpyFromSymbol(out, magdev::g_phase_clk, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(magdev::g_phase_clk, z, sizeof(z)) != cudaSuccess) return -1; }
+  return 0;
+}
+#endif
