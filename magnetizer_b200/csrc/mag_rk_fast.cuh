@@ -71,6 +71,7 @@ struct RkShared {
   FastCall call;
   GuardK gk[2];
   unsigned red[8];                                        // block maxima (high words)
+  double stage_dg[3], stage_dz[3];                        // dt*gamma, dt*zeta of the three RK stages (looped stage body)
   // lines: [buffer][variable][4 + global point index] with row length MAG_LINE_S or MAG_LINE_L
   // (4 pad points each side, so that a thread's window -- own points +-3 -- is covered by
   // 16-byte aligned vector loads); for COEF_WSMEM the stencil weights [k][slot*64 + thread]

@@ -44,6 +44,9 @@ namespace magdev {
 // when every warp of an SM runs the same variant, but eight warps running eight different
 // 15-20 KB loops thrash the instruction caches (ncu: stall_no_instruction 15 cycles per
 // issue on the synthetic catalogue), so the default is the looped body.
+#ifndef MAG_W4_MODE
+#define MAG_W4_MODE WM_WSM   // same speed as WM_REGS on the looped body, smaller code, no spills
+#endif
 #ifndef MAG_WARP_SPECIALIZE_DEFAULT
 #define MAG_WARP_SPECIALIZE_DEFAULT 0
 #endif
@@ -151,14 +154,25 @@ __device__ __forceinline__ void outer_ghosts(WarpState<PPL, MODE>& S, const int 
 // JM = -1: in register jm (one warp-uniform switch).  The inner one, p = 0, sits in register
 // WARP_J0 = 3 of lane 0, so that p = -3..-1 are its (inert) registers 0..2.
 #define WARP_J0 3
+// 64-bit shuffles as two explicit 32-bit ones (the compiler's own lowering of a double shuffle
+// lands the halves in swapped registers and then swaps them back with three LOP3 each)
+__device__ __forceinline__ double shfl_down1(double x) {
+  const int lo = __shfl_down_sync(FULL, __double2loint(x), 1), hi = __shfl_down_sync(FULL, __double2hiint(x), 1);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up1(double x) {
+  const int lo = __shfl_up_sync(FULL, __double2loint(x), 1), hi = __shfl_up_sync(FULL, __double2hiint(x), 1);
+  return __hiloint2double(hi, lo);
+}
+
 template <int PPL, int MODE, int JM>
 __device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int lane, const int tm, const int jm) {
 #pragma unroll
   for (int v = 0; v < 3; v++) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      S.hr[v][k] = __shfl_down_sync(FULL, S.f[v][k], 1);
-      S.hl[v][k] = __shfl_up_sync(FULL, S.f[v][PPL - 3 + k], 1);
+      S.hr[v][k] = shfl_down1(S.f[v][k]);
+      S.hl[v][k] = shfl_up1(S.f[v][PPL - 3 + k]);
     }
   }
   // inner end: the ghost entries of p = 0 (all three), of p = 1 (p = -2) and of p = 2 (p = -1)
@@ -188,23 +202,23 @@ __device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int
   }
 }
 
-// One Runge-Kutta stage on the window (hl, f, hr) that warp_exchange left behind.
+// One Runge-Kutta stage on the window (hl, f, hr) that warp_exchange left behind.  Phase 1
+// evaluates the 3*PPL stencil chains (independent of each other: the scheduler interleaves
+// them; own registers first, halo entries last, so that they overlap the tail of the
+// exchange); phase 2 does the point-wise terms and updates f and ftmp IN PLACE -- every old
+// value has been consumed by then, so no register has to be copied back at the loop edge.
 template <int PPL, int MODE, bool LAST>
-__device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsigned wsa, const double2* __restrict__ tab, const int lane,
-                                           const double dg, const double dz, unsigned& mBs, unsigned& mBu,
-                                           unsigned& mAs, unsigned& mAu, double* __restrict__ alp_out, const int g0, const int m) {
-  double win[3][PPL + 6];
-#pragma unroll
-  for (int v = 0; v < 3; v++) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) { win[v][k] = S.hl[v][k]; win[v][PPL + 3 + k] = S.hr[v][k]; }
-#pragma unroll
-    for (int j = 0; j < PPL; j++) win[v][3 + j] = S.f[v][j];
-  }
-  // ---- point by point: three stencil chains, point-wise terms, Runge-Kutta update
+__device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsigned wsa, const double2* __restrict__ tab,
+                                           const double dg, const double dz, unsigned& mBs, unsigned& mBu, unsigned& mAs,
+                                           unsigned& mAu) {
+  auto W3 = [&](int v, int i) -> double {   // window entry i of variable v (compile-time i after unrolling)
+    return i < 3 ? S.hl[v][i < 3 ? i : 0] : (i < PPL + 3 ? S.f[v][(i >= 3 && i < PPL + 3) ? i - 3 : 0] : S.hr[v][i >= PPL + 3 ? i - PPL - 3 : 0]);
+  };
+  double acc[3][PPL];
+  // ---- phase 1: stencil chains L(Br), L(Bp) + floor constant, alp_m chain
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
-    double w[8], c_ca, c_gs, c_c0, c_fk, c_ak, c_p3, c_qc;
+    double w[8];
     if (MODE == WM_REGS) {
 #pragma unroll
       for (int k = 0; k < 8; k++) w[k] = S.w[MODE == WM_REGS ? j : 0][k];
@@ -215,13 +229,32 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
         w[2 * q] = t.x; w[2 * q + 1] = t.y;
       }
     }
+    const double c_c0 = MODE == WM_ALLG ? ldg_pair(tab + GSLOT2(j, 5)).x : S.c0[MODE == WM_ALLG ? 0 : j];
+    double a0 = w[3] * S.f[0][j], a1 = fma(w[3], S.f[1][j], c_c0), a2 = w[7] * S.f[2][j];
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {   // pass 0: neighbours in own registers, pass 1: halo entries
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        const int i = j + k;
+        const bool own = i >= 3 && i < PPL + 3;
+        if (k != 3 && own == (pass == 0)) {
+          a0 = fma(w[k], W3(0, i), a0); a1 = fma(w[k], W3(1, i), a1); a2 = fma(w[k], W3(2, i), a2);
+        }
+      }
+    }
+    acc[0][j] = a0; acc[1][j] = a1; acc[2][j] = a2;
+  }
+  // ---- phase 2: point-wise terms and the Runge-Kutta update, in place
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    double c_ca, c_gs, c_fk, c_ak, c_p3, c_qc;
     if (MODE == WM_ALLG) {
       const double2 t4 = ldg_pair(tab + GSLOT2(j, 4)), t5 = ldg_pair(tab + GSLOT2(j, 5)), t6 = ldg_pair(tab + GSLOT2(j, 6));
       const double2 t7 = ldg_pair(tab + GSLOT2(j, 7));
-      c_ca = t4.x; c_gs = t4.y; c_c0 = t5.x; c_fk = t5.y; c_ak = t6.x; c_p3 = t6.y; c_qc = t7.x;
+      c_ca = t4.x; c_gs = t4.y; c_fk = t5.y; c_ak = t6.x; c_p3 = t6.y; c_qc = t7.x;
     } else {
       constexpr int jj = MODE == WM_ALLG ? 0 : 1;
-      c_ca = S.ca[j * jj]; c_gs = S.gs[j * jj]; c_c0 = S.c0[j * jj]; c_fk = S.fk[j * jj]; c_ak = S.ak[j * jj];
+      c_ca = S.ca[j * jj]; c_gs = S.gs[j * jj]; c_fk = S.fk[j * jj]; c_ak = S.ak[j * jj];
       if (MODE == WM_WSM2) {
         const double2 t = lds_pair(wsa + 16u * WSLOT2(j, 4));
         c_p3 = t.x; c_qc = t.y;
@@ -229,21 +262,13 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
         c_p3 = S.p3[MODE >= WM_WSM2 ? 0 : j]; c_qc = S.qc[MODE >= WM_WSM2 ? 0 : j];
       }
     }
-    const double Br = win[0][3 + j], Bp = win[1][3 + j], am = win[2][3 + j];
-    // chains start at the centre and work outwards, so that the halo terms come last
-    double a0 = w[3] * Br, a1 = fma(w[3], Bp, c_c0), a2 = w[7] * am;
-#pragma unroll
-    for (int d = 1; d <= 3; d++) {
-      a0 = fma(w[3 - d], win[0][j + 3 - d], a0); a1 = fma(w[3 - d], win[1][j + 3 - d], a1); a2 = fma(w[3 - d], win[2][j + 3 - d], a2);
-      a0 = fma(w[3 + d], win[0][j + 3 + d], a0); a1 = fma(w[3 + d], win[1][j + 3 + d], a1); a2 = fma(w[3 + d], win[2][j + 3 + d], a2);
-    }
+    const double Br = S.f[0][j], Bp = S.f[1][j], am = S.f[2][j];
     const double a = c_ak + am;
-    if (alp_out) { const int g = g0 + j; if (g >= MAG_NGHOST && g <= m) alp_out[g] = a; }
-    const double p0 = fma(-(c_ca * a), Bp, a0);
-    const double p1 = fma(c_fk, am, fma(c_gs, Br, a1));
+    const double p0 = fma(-(c_ca * a), Bp, acc[0][j]);
+    const double p1 = fma(c_fk, am, fma(c_gs, Br, acc[1][j]));
     const double B2 = fma(Br, Br, Bp * Bp);
     const double em = fma(c_qc * fast_sqrt_abs(a), Br * Bp, a * B2);
-    const double p2 = fma(c_p3, em, a2);
+    const double p2 = fma(c_p3, em, acc[2][j]);
     const double n0 = fma(dg, p0, S.ft[0][j]), n1 = fma(dg, p1, S.ft[1][j]), n2 = fma(dg, p2, S.ft[2][j]);
     S.f[0][j] = n0; S.f[1][j] = n1; S.f[2][j] = n2;
     if (LAST) { S.ft[0][j] = n0; S.ft[1][j] = n1; S.ft[2][j] = n2; }
@@ -253,6 +278,19 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
     mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(n0), (unsigned)__double2hiint(n1));
     mAs = (unsigned)max((int)mAs, __double2hiint(n2));
     mAu = max(mAu, (unsigned)__double2hiint(n2));
+  }
+}
+
+// alp = alp_k + alp_m as the last pde call of the snapshot sees it (an output row); called once
+// per snapshot, kept out of line so that the time loop only carries one predicate for it
+template <int PPL>
+struct AmRow { double v[PPL]; };
+template <int PPL>
+__device__ __noinline__ void save_alp_row(const double* __restrict__ akp, double* __restrict__ alp, const int g0, const int m, const AmRow<PPL> am) {
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    const int g = g0 + j;
+    if (g >= MAG_NGHOST && g <= m) alp[g] = akp[g] + am.v[j];
   }
 }
 
@@ -339,6 +377,12 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
       for (int v = 0; v < 3; v++) S.ft[v][j] = S.f[v][j];
     warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
   };
+  auto save_alp = [&]() {
+    AmRow<PPL> r;
+#pragma unroll
+    for (int j = 0; j < PPL; j++) r.v[j] = S.f[2][j];
+    save_alp_row<PPL>(WA(F_AK), WA(A_ALP), g0, m, r);
+  };
   load_signed_floor();
   load_state();
   __syncwarp();
@@ -346,6 +390,11 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
 
   const double dg0 = dt * (8.0 / 15), dg1 = dt * (5.0 / 12), dg2 = dt * (3.0 / 4);
   const double dz0 = dt * (-17.0 / 60), dz1 = dt * (-5.0 / 12);
+  if (lane == 0) {
+    rs->stage_dg[0] = dg0; rs->stage_dg[1] = dg1; rs->stage_dg[2] = dg2;
+    rs->stage_dz[0] = dz0; rs->stage_dz[1] = dz1; rs->stage_dz[2] = 0.0;
+  }
+  __syncwarp();
   const double dtg = dt * G.a->U.t0_Gyr, t_Gyr = G.t_Gyr, tmk = G.a->P.p_floor_kappa * G.tau_min;
   double t = G.t, t_last = G.t_last_sign_choice;
   int sign_nx = G.sign_nx;
@@ -402,19 +451,21 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
         if (lane == 0) { atomicAdd(&g_phase_clk[8], (unsigned long long)(clock64() - _r0)); atomicAdd(&g_phase_clk[9], 1ull); }
 #endif
       }
-      double* alp_out = (jt + s == nsteps) ? WA(A_ALP) : nullptr;
+      const bool last_step = jt + s == nsteps;
       if (JM >= 0 || PPL <= MAG_WARP_UNROLL_MAXPPL) {  // three stages unrolled: their shuffles and chains overlap
-        warp_stage<PPL, MODE, false>(S, wsa, tab, lane, dg0, dz0, mBs, mBu, mAs, mAu, nullptr, g0, m);
+        warp_stage<PPL, MODE, false>(S, wsa, tab, dg0, dz0, mBs, mBu, mAs, mAu);
         warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
-        warp_stage<PPL, MODE, false>(S, wsa, tab, lane, dg1, dz1, mBs, mBu, mAs, mAu, nullptr, g0, m);
+        warp_stage<PPL, MODE, false>(S, wsa, tab, dg1, dz1, mBs, mBu, mAs, mAu);
         warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
-        warp_stage<PPL, MODE, true>(S, wsa, tab, lane, dg2, 0.0, mBs, mBu, mAs, mAu, alp_out, g0, m);
+        if (last_step) save_alp();
+        warp_stage<PPL, MODE, true>(S, wsa, tab, dg2, 0.0, mBs, mBu, mAs, mAu);
         warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
       } else {         // one stage body, looped: a three times smaller instruction footprint
 #pragma unroll 1
         for (int st = 0; st < 3; st++) {
-          const double dg = st == 0 ? dg0 : (st == 1 ? dg1 : dg2), dz = st == 0 ? dz0 : (st == 1 ? dz1 : 0.0);
-          warp_stage<PPL, MODE, false>(S, wsa, tab, lane, dg, dz, mBs, mBu, mAs, mAu, st == 2 ? alp_out : nullptr, g0, m);
+          const double dg = rs->stage_dg[st], dz = rs->stage_dz[st];
+          if (st == 2 && last_step) save_alp();
+          warp_stage<PPL, MODE, false>(S, wsa, tab, dg, dz, mBs, mBu, mAs, mAu);
           warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
         }
       }
@@ -510,9 +561,9 @@ __device__ __forceinline__ bool warp_path_applies(const Gal& G) {
 __device__ __forceinline__ bool warp_dispatch(Gal& G, RkShared* rs) {
   // the default grid (p_nx_ref = 101: nx = 107, most of the work) has its own instantiation with
   // a compile-time outer alignment and the three stages unrolled
-  if (MAG_WARP_SPECIALIZE_DEFAULT && G.nx == 107) return warp_loop<4, WM_REGS, 3>(G, rs);
+  if (MAG_WARP_SPECIALIZE_DEFAULT && G.nx == 107) return warp_loop<4, MAG_W4_MODE, 3>(G, rs);
   switch (warp_ppl(G.nx)) {
-    case 4: return warp_loop<4, WM_REGS, -1>(G, rs);
+    case 4: return warp_loop<4, MAG_W4_MODE, -1>(G, rs);
     case 5: return warp_loop<5, WM_WSM, -1>(G, rs);
     case 6: return warp_loop<6, WM_WSM2, -1>(G, rs);
     case 8: return warp_loop<8, WM_ALLG, -1>(G, rs);
