@@ -202,11 +202,16 @@ __device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int
   }
 }
 
-// One Runge-Kutta stage on the window (hl, f, hr) that warp_exchange left behind.  Phase 1
-// evaluates the 3*PPL stencil chains (independent of each other: the scheduler interleaves
-// them; own registers first, halo entries last, so that they overlap the tail of the
-// exchange); phase 2 does the point-wise terms and updates f and ftmp IN PLACE -- every old
-// value has been consumed by then, so no register has to be copied back at the loop edge.
+// One Runge-Kutta stage on the window (hl, f, hr) that warp_exchange left behind, written as
+// three phases whose statements are interleaved ACROSS the points of the lane, so that the
+// scheduler finds 4+ independent FP64 instructions at every moment (DFMA latency is 8 cycles at
+// an issue interval of 2; with two warps per scheduler the chains have to overlap inside a warp):
+//   phase 0  point-wise non-linear terms (own values only; overlaps the tail of the exchange
+//            and the first coefficient loads)
+//   phase 1  the 3*PPL stencil chains, two points at a time, own registers before halo
+//            entries, the coefficient pairs of the next two points in flight
+//   phase 2  right-hand sides and the Runge-Kutta update of f and ftmp IN PLACE -- every old
+//            value has been consumed by then, so nothing is copied back at the loop edge.
 template <int PPL, int MODE, bool LAST>
 __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsigned wsa, const double2* __restrict__ tab,
                                            const double dg, const double dz, unsigned& mBs, unsigned& mBu, unsigned& mAs,
@@ -214,11 +219,7 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
   auto W3 = [&](int v, int i) -> double {   // window entry i of variable v (compile-time i after unrolling)
     return i < 3 ? S.hl[v][i < 3 ? i : 0] : (i < PPL + 3 ? S.f[v][(i >= 3 && i < PPL + 3) ? i - 3 : 0] : S.hr[v][i >= PPL + 3 ? i - PPL - 3 : 0]);
   };
-  double acc[3][PPL];
-  // ---- phase 1: stencil chains L(Br), L(Bp) + floor constant, alp_m chain
-#pragma unroll
-  for (int j = 0; j < PPL; j++) {
-    double w[8];
+  auto load_w = [&](int j, double* w) {
     if (MODE == WM_REGS) {
 #pragma unroll
       for (int k = 0; k < 8; k++) w[k] = S.w[MODE == WM_REGS ? j : 0][k];
@@ -229,55 +230,111 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
         w[2 * q] = t.x; w[2 * q + 1] = t.y;
       }
     }
-    const double c_c0 = MODE == WM_ALLG ? ldg_pair(tab + GSLOT2(j, 5)).x : S.c0[MODE == WM_ALLG ? 0 : j];
-    double a0 = w[3] * S.f[0][j], a1 = fma(w[3], S.f[1][j], c_c0), a2 = w[7] * S.f[2][j];
+  };
+  constexpr int NG = (PPL + 1) / 2;   // groups of two points
+  double wq[2][2][8];                 // [buffer][point of the group][weight]
+  load_w(0, wq[0][0]);
+  if (PPL > 1) load_w(1, wq[0][1]);
+  // ---- phase 0: caa = ca*alp and em = alp*(Br^2+Bp^2) + qc*sqrt|alp|*Br*Bp
+  double caa[PPL], em[PPL], c_gs[PPL], c_fk[PPL], c_p3[PPL], c_c0[PPL];
+  {
+    double al[PPL], B2[PPL], bb[PPL], g[PPL], h[PPL], c_qc[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+      double c_ca, c_ak;
+      if (MODE == WM_ALLG) {
+        const double2 t4 = ldg_pair(tab + GSLOT2(j, 4)), t5 = ldg_pair(tab + GSLOT2(j, 5)), t6 = ldg_pair(tab + GSLOT2(j, 6));
+        const double2 t7 = ldg_pair(tab + GSLOT2(j, 7));
+        c_ca = t4.x; c_gs[j] = t4.y; c_c0[j] = t5.x; c_fk[j] = t5.y; c_ak = t6.x; c_p3[j] = t6.y; c_qc[j] = t7.x;
+      } else {
+        constexpr int jj = MODE == WM_ALLG ? 0 : 1;
+        c_ca = S.ca[j * jj]; c_gs[j] = S.gs[j * jj]; c_c0[j] = S.c0[j * jj]; c_fk[j] = S.fk[j * jj]; c_ak = S.ak[j * jj];
+        if (MODE == WM_WSM2) {
+          const double2 t = lds_pair(wsa + 16u * WSLOT2(j, 4));
+          c_p3[j] = t.x; c_qc[j] = t.y;
+        } else {
+          c_p3[j] = S.p3[MODE >= WM_WSM2 ? 0 : j]; c_qc[j] = S.qc[MODE >= WM_WSM2 ? 0 : j];
+        }
+      }
+      al[j] = c_ak + S.f[2][j];
+      caa[j] = c_ca * al[j];
+    }
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {   // sqrt|alp|: MUFU.RSQ64H seed + one Goldschmidt step (fast_sqrt_abs), interleaved
+      int hi = __double2hiint(al[j]) & 0x7fffffff;
+      hi = max(hi, 0x00200000);
+      const double x = __hiloint2double(hi, __double2loint(al[j]));
+      double r;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+      g[j] = x * r; h[j] = 0.5 * r;
+    }
+#pragma unroll
+    for (int j = 0; j < PPL; j++) { B2[j] = S.f[1][j] * S.f[1][j]; bb[j] = S.f[0][j] * S.f[1][j]; }
+#pragma unroll
+    for (int j = 0; j < PPL; j++) { h[j] = fma(-g[j], h[j], 0.5); B2[j] = fma(S.f[0][j], S.f[0][j], B2[j]); }
+#pragma unroll
+    for (int j = 0; j < PPL; j++) { g[j] = fma(g[j], h[j], g[j]); B2[j] = al[j] * B2[j]; }
+#pragma unroll
+    for (int j = 0; j < PPL; j++) g[j] = c_qc[j] * g[j];
+#pragma unroll
+    for (int j = 0; j < PPL; j++) em[j] = fma(g[j], bb[j], B2[j]);
+  }
+  // ---- phase 1: stencil chains L(Br), L(Bp) + floor constant, alp_m chain
+  double acc[3][PPL];
+#pragma unroll
+  for (int gi = 0; gi < NG; gi++) {
+    const int ja = 2 * gi, jb = 2 * gi + 1;
+    const bool hasb = jb < PPL;
+    const int cur = gi & 1;
+    if (gi + 1 < NG) {   // coefficient pairs of the next group
+      load_w(2 * gi + 2, wq[cur ^ 1][0]);
+      if (2 * gi + 3 < PPL) load_w(2 * gi + 3, wq[cur ^ 1][1]);
+    }
+    const double* wa = wq[cur][0];
+    const double* wb = wq[cur][1];
+    double a0 = wa[3] * S.f[0][ja], a1 = fma(wa[3], S.f[1][ja], c_c0[ja]), a2 = wa[7] * S.f[2][ja];
+    double b0 = 0, b1 = 0, b2 = 0;
+    if (hasb) { b0 = wb[3] * S.f[0][hasb ? jb : 0]; b1 = fma(wb[3], S.f[1][hasb ? jb : 0], c_c0[hasb ? jb : 0]); b2 = wb[7] * S.f[2][hasb ? jb : 0]; }
 #pragma unroll
     for (int pass = 0; pass < 2; pass++) {   // pass 0: neighbours in own registers, pass 1: halo entries
 #pragma unroll
       for (int k = 0; k < 7; k++) {
-        const int i = j + k;
-        const bool own = i >= 3 && i < PPL + 3;
-        if (k != 3 && own == (pass == 0)) {
-          a0 = fma(w[k], W3(0, i), a0); a1 = fma(w[k], W3(1, i), a1); a2 = fma(w[k], W3(2, i), a2);
+        if (k == 3) continue;
+        const int ia = ja + k, ib = jb + k;
+        if ((ia >= 3 && ia < PPL + 3) == (pass == 0)) {
+          a0 = fma(wa[k], W3(0, ia), a0); a1 = fma(wa[k], W3(1, ia), a1); a2 = fma(wa[k], W3(2, ia), a2);
+        }
+        if (hasb && (ib >= 3 && ib < PPL + 3) == (pass == 0)) {
+          b0 = fma(wb[k], W3(0, ib), b0); b1 = fma(wb[k], W3(1, ib), b1); b2 = fma(wb[k], W3(2, ib), b2);
         }
       }
     }
-    acc[0][j] = a0; acc[1][j] = a1; acc[2][j] = a2;
+    acc[0][ja] = a0; acc[1][ja] = a1; acc[2][ja] = a2;
+    if (hasb) { acc[0][hasb ? jb : 0] = b0; acc[1][hasb ? jb : 0] = b1; acc[2][hasb ? jb : 0] = b2; }
   }
-  // ---- phase 2: point-wise terms and the Runge-Kutta update, in place
+  // ---- phase 2: right-hand sides and the Runge-Kutta update, in place
+  double p0[PPL], p1[PPL], p2[PPL];
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
-    double c_ca, c_gs, c_fk, c_ak, c_p3, c_qc;
-    if (MODE == WM_ALLG) {
-      const double2 t4 = ldg_pair(tab + GSLOT2(j, 4)), t5 = ldg_pair(tab + GSLOT2(j, 5)), t6 = ldg_pair(tab + GSLOT2(j, 6));
-      const double2 t7 = ldg_pair(tab + GSLOT2(j, 7));
-      c_ca = t4.x; c_gs = t4.y; c_fk = t5.y; c_ak = t6.x; c_p3 = t6.y; c_qc = t7.x;
-    } else {
-      constexpr int jj = MODE == WM_ALLG ? 0 : 1;
-      c_ca = S.ca[j * jj]; c_gs = S.gs[j * jj]; c_fk = S.fk[j * jj]; c_ak = S.ak[j * jj];
-      if (MODE == WM_WSM2) {
-        const double2 t = lds_pair(wsa + 16u * WSLOT2(j, 4));
-        c_p3 = t.x; c_qc = t.y;
-      } else {
-        c_p3 = S.p3[MODE >= WM_WSM2 ? 0 : j]; c_qc = S.qc[MODE >= WM_WSM2 ? 0 : j];
-      }
-    }
-    const double Br = S.f[0][j], Bp = S.f[1][j], am = S.f[2][j];
-    const double a = c_ak + am;
-    const double p0 = fma(-(c_ca * a), Bp, acc[0][j]);
-    const double p1 = fma(c_fk, am, fma(c_gs, Br, acc[1][j]));
-    const double B2 = fma(Br, Br, Bp * Bp);
-    const double em = fma(c_qc * fast_sqrt_abs(a), Br * Bp, a * B2);
-    const double p2 = fma(c_p3, em, acc[2][j]);
-    const double n0 = fma(dg, p0, S.ft[0][j]), n1 = fma(dg, p1, S.ft[1][j]), n2 = fma(dg, p2, S.ft[2][j]);
-    S.f[0][j] = n0; S.f[1][j] = n1; S.f[2][j] = n2;
-    if (LAST) { S.ft[0][j] = n0; S.ft[1][j] = n1; S.ft[2][j] = n2; }
-    else { S.ft[0][j] = fma(dz, p0, n0); S.ft[1][j] = fma(dz, p1, n1); S.ft[2][j] = fma(dz, p2, n2); }
+    p0[j] = fma(-caa[j], S.f[1][j], acc[0][j]);
+    p1[j] = fma(c_gs[j], S.f[0][j], acc[1][j]);
+    p2[j] = fma(c_p3[j], em[j], acc[2][j]);
+  }
+#pragma unroll
+  for (int j = 0; j < PPL; j++) p1[j] = fma(c_fk[j], S.f[2][j], p1[j]);
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    S.f[0][j] = fma(dg, p0[j], S.ft[0][j]); S.f[1][j] = fma(dg, p1[j], S.ft[1][j]); S.f[2][j] = fma(dg, p2[j], S.ft[2][j]);
+  }
+#pragma unroll
+  for (int j = 0; j < PPL; j++) {
+    if (LAST) { S.ft[0][j] = S.f[0][j]; S.ft[1][j] = S.f[1][j]; S.ft[2][j] = S.f[2][j]; }
+    else { S.ft[0][j] = fma(dz, p0[j], S.f[0][j]); S.ft[1][j] = fma(dz, p1[j], S.f[1][j]); S.ft[2][j] = fma(dz, p2[j], S.f[2][j]); }
     // |x| maxima on the high words: signed max catches the positive values, unsigned max the negative ones
-    mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(n0), __double2hiint(n1));
-    mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(n0), (unsigned)__double2hiint(n1));
-    mAs = (unsigned)max((int)mAs, __double2hiint(n2));
-    mAu = max(mAu, (unsigned)__double2hiint(n2));
+    mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(S.f[0][j]), __double2hiint(S.f[1][j]));
+    mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(S.f[0][j]), (unsigned)__double2hiint(S.f[1][j]));
+    mAs = (unsigned)max((int)mAs, __double2hiint(S.f[2][j]));
+    mAu = max(mAu, (unsigned)__double2hiint(S.f[2][j]));
   }
 }
 
