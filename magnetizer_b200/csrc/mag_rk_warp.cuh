@@ -154,6 +154,9 @@ __device__ __forceinline__ void outer_ghosts(WarpState<PPL, MODE>& S, const int 
 // JM = -1: in register jm (one warp-uniform switch).  The inner one, p = 0, sits in register
 // WARP_J0 = 3 of lane 0, so that p = -3..-1 are its (inert) registers 0..2.
 #define WARP_J0 3
+// up to this PPL the stage applies the ghost entries after its phase 0; the large-grid variants
+// apply them right after the exchange (fewer values live across the stage: no spills)
+#define WARP_LATE_GHOSTS_MAXPPL 6
 // 64-bit shuffles as two explicit 32-bit ones (the compiler's own lowering of a double shuffle
 // lands the halves in swapped registers and then swaps them back with three LOP3 each)
 __device__ __forceinline__ double shfl_down1(double x) {
@@ -165,8 +168,8 @@ __device__ __forceinline__ double shfl_up1(double x) {
   return __hiloint2double(hi, lo);
 }
 
-template <int PPL, int MODE, int JM>
-__device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int lane, const int tm, const int jm) {
+template <int PPL, int MODE>
+__device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S) {
 #pragma unroll
   for (int v = 0; v < 3; v++) {
 #pragma unroll
@@ -175,6 +178,11 @@ __device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int
       S.hl[v][k] = shfl_up1(S.f[v][PPL - 3 + k]);
     }
   }
+}
+// The Neumann ghost entries of alp_m, applied by the stage after its phase 0 (so that the
+// shuffles of warp_exchange have landed by then).
+template <int PPL, int MODE, int JM>
+__device__ __forceinline__ void warp_ghosts(WarpState<PPL, MODE>& S, const int lane, const int tm, const int jm) {
   // inner end: the ghost entries of p = 0 (all three), of p = 1 (p = -2) and of p = 2 (p = -1)
   // live in the windows of the lanes that own those points
   constexpr int J0 = WARP_J0;
@@ -185,6 +193,8 @@ __device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int
   // outer end
   if (JM >= 0) {
     outer_ghosts<PPL, MODE, (JM >= 0 ? JM : 0)>(S, lane, tm);
+  } else if (jm == PPL - 1) {   // the default grid (nx = 107) and every other grid that fills its last lane
+    outer_ghosts<PPL, MODE, PPL - 1>(S, lane, tm);
   } else {
     switch (jm) {
       case 0: outer_ghosts<PPL, MODE, 0>(S, lane, tm); break;
@@ -196,8 +206,7 @@ __device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int
       case 6: if (PPL > 6) outer_ghosts<PPL, MODE, (PPL > 6 ? 6 : 0)>(S, lane, tm); break;
       case 7: if (PPL > 7) outer_ghosts<PPL, MODE, (PPL > 7 ? 7 : 0)>(S, lane, tm); break;
       case 8: if (PPL > 8) outer_ghosts<PPL, MODE, (PPL > 8 ? 8 : 0)>(S, lane, tm); break;
-      case 9: if (PPL > 9) outer_ghosts<PPL, MODE, (PPL > 9 ? 9 : 0)>(S, lane, tm); break;
-      default: if (PPL > 10) outer_ghosts<PPL, MODE, (PPL > 10 ? 10 : 0)>(S, lane, tm); break;
+      default: if (PPL > 9) outer_ghosts<PPL, MODE, (PPL > 9 ? 9 : 0)>(S, lane, tm); break;
     }
   }
 }
@@ -212,10 +221,10 @@ __device__ __forceinline__ void warp_exchange(WarpState<PPL, MODE>& S, const int
 //            entries, the coefficient pairs of the next two points in flight
 //   phase 2  right-hand sides and the Runge-Kutta update of f and ftmp IN PLACE -- every old
 //            value has been consumed by then, so nothing is copied back at the loop edge.
-template <int PPL, int MODE, bool LAST>
-__device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsigned wsa, const double2* __restrict__ tab,
-                                           const double dg, const double dz, unsigned& mBs, unsigned& mBu, unsigned& mAs,
-                                           unsigned& mAu) {
+template <int PPL, int MODE, int JM, bool LAST>
+__device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsigned wsa, const double2* __restrict__ tab, const int lane,
+                                           const int tm, const int jm, const double dg, const double dz, unsigned& mBs,
+                                           unsigned& mBu, unsigned& mAs, unsigned& mAu) {
   auto W3 = [&](int v, int i) -> double {   // window entry i of variable v (compile-time i after unrolling)
     return i < 3 ? S.hl[v][i < 3 ? i : 0] : (i < PPL + 3 ? S.f[v][(i >= 3 && i < PPL + 3) ? i - 3 : 0] : S.hr[v][i >= PPL + 3 ? i - PPL - 3 : 0]);
   };
@@ -279,6 +288,7 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
 #pragma unroll
     for (int j = 0; j < PPL; j++) em[j] = fma(g[j], bb[j], B2[j]);
   }
+  if (PPL <= WARP_LATE_GHOSTS_MAXPPL) warp_ghosts<PPL, MODE, JM>(S, lane, tm, jm);
   // ---- phase 1: stencil chains L(Br), L(Bp) + floor constant, alp_m chain
   double acc[3][PPL];
 #pragma unroll
@@ -432,7 +442,8 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
     for (int j = 0; j < PPL; j++)
 #pragma unroll
       for (int v = 0; v < 3; v++) S.ft[v][j] = S.f[v][j];
-    warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+    warp_exchange<PPL, MODE>(S);
+    if (PPL > WARP_LATE_GHOSTS_MAXPPL) warp_ghosts<PPL, MODE, JM>(S, lane, tm, jm);
   };
   auto save_alp = [&]() {
     AmRow<PPL> r;
@@ -510,20 +521,21 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
       }
       const bool last_step = jt + s == nsteps;
       if (JM >= 0 || PPL <= MAG_WARP_UNROLL_MAXPPL) {  // three stages unrolled: their shuffles and chains overlap
-        warp_stage<PPL, MODE, false>(S, wsa, tab, dg0, dz0, mBs, mBu, mAs, mAu);
-        warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
-        warp_stage<PPL, MODE, false>(S, wsa, tab, dg1, dz1, mBs, mBu, mAs, mAu);
-        warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+        warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg0, dz0, mBs, mBu, mAs, mAu);
+        warp_exchange<PPL, MODE>(S);
+        warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg1, dz1, mBs, mBu, mAs, mAu);
+        warp_exchange<PPL, MODE>(S);
         if (last_step) save_alp();
-        warp_stage<PPL, MODE, true>(S, wsa, tab, dg2, 0.0, mBs, mBu, mAs, mAu);
-        warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+        warp_stage<PPL, MODE, JM, true>(S, wsa, tab, lane, tm, jm, dg2, 0.0, mBs, mBu, mAs, mAu);
+        warp_exchange<PPL, MODE>(S);
       } else {         // one stage body, looped: a three times smaller instruction footprint
 #pragma unroll 1
         for (int st = 0; st < 3; st++) {
           const double dg = rs->stage_dg[st], dz = rs->stage_dz[st];
           if (st == 2 && last_step) save_alp();
-          warp_stage<PPL, MODE, false>(S, wsa, tab, dg, dz, mBs, mBu, mAs, mAu);
-          warp_exchange<PPL, MODE, JM>(S, lane, tm, jm);
+          warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg, dz, mBs, mBu, mAs, mAu);
+          warp_exchange<PPL, MODE>(S);
+          if (PPL > WARP_LATE_GHOSTS_MAXPPL) warp_ghosts<PPL, MODE, JM>(S, lane, tm, jm);
         }
       }
       // t = t + dt*gam1 ; ttmp = t + dt*zet1 ; t = ttmp + dt*gam2 ; ttmp = t + dt*zet2 ; t = ttmp + dt*gam3
