@@ -1,27 +1,32 @@
 // mag_rk_warp.cuh -- the time-stepping loop of one snapshot (dynamo.f90:168-212) on ONE WARP
-// per galaxy, state and coefficients in registers, halo exchange by warp shuffles.
+// per galaxy: the state (Br, Bp, alp_m, ftmp) lives in registers for the whole snapshot, the
+// halo is exchanged by warp shuffles, there is no barrier and no shared-memory line.
 //
 // Layout.  The live points of the grid are g = 3 .. m (m = nx-4; gutsdynamo.f90:55-86:
 // g = 3 and g = m are the Dirichlet points of Br, Bp; g < 3 and g > m are ghost zones).
-// With p = g - 3 in [0, P] (P = nx-7), slot s = p + 2 belongs to lane s / PPL, register
-// j = s % PPL: the inner end is fixed (p = 0 in register 2 of lane 0), the outer end falls
-// on register jm = (P+2) % PPL of lane tm = (P+2) / PPL, a run-time position that only two
-// small warp-uniform switches per stage look at.  The loop is therefore instantiated once
-// per PPL and not once per alignment: all the warps of an SM that work on grids of the same
-// size class share one loop body in the instruction caches (with one instantiation per
-// alignment, ncu showed 15 stall_no_instruction cycles per issue on the mixed catalogue).
-// Ghost values are never stored.  Slots outside the live range are inert (all coefficients
-// zero, value 0), which is exactly what Br and Bp need once the boundary conditions are folded
-// into the stencil weights (fold_boundary_weights); the four alp_m ghost entries that keep a
-// non-zero weight are copied inside the window of the lane that uses them.
+// With p = g - 3 in [0, P] (P = nx-7), slot s = p + 3 belongs to lane s / PPL, register
+// j = s % PPL: the inner end is fixed (p = 0 in register 3 of lane 0, p = -3..-1 in its
+// registers 0..2), the outer end falls on register jm = (P+3) % PPL of lane tm = (P+3) / PPL,
+// a run-time position that one warp-uniform branch per stage looks at.  The loop is
+// therefore instantiated once per PPL and not once per alignment, and the three Runge-Kutta
+// stages share ONE looped body (ftmp == f at the start of a step): the two warps of an SM
+// sub-partition then fit into its instruction cache even when they work on different grid
+// classes.  (Measured: with one unrolled 14 KB loop per alignment ncu shows 15
+// stall_no_instruction cycles per issue on the mixed catalogue and the throughput drops 4x,
+// although the same loops run 40 % faster when all warps of the SM execute the same one.)
 //
-// Per stage and thread: 36 SHFL (3 variables x 6 halo values x 2 words), then for each of the
-// PPL points the folded right-hand side of mag_rk_fast.cuh with two more foldings
+// Boundary conditions (impose_bc) cost nothing for Br and Bp: slots outside the live range
+// are inert (all coefficients zero, value 0) and the mirror condition is folded into the
+// stencil weights (fold_boundary_weights), which also keeps Br = Bp = 0 at the Dirichlet
+// points without ever resetting them.  alp_m needs three mirrored values per end, copied into
+// the window of the lanes that use them (warp_ghosts).
+//
+// Per stage and thread: 36 SHFL (3 variables x 6 halo values x 2 words) and, per point, the
+// folded right-hand side of mag_rk_fast.cuh with two more foldings
 //   fb*(1 + kdc*alp) = c0 + fk*alp_m ,  c0 = fb*(1 + kdc*alp_k)  (c0 seeds the L(Bp) chain)
 //   R_kappa = 1: w0a*alp_m seeds the alp_m stencil chain
-// = 43 FP64 instructions per point and stage, no shared-memory traffic, no barrier.
-// PPL = 4 keeps all 15 per-point coefficients in registers (nx <= 134); PPL = 5, 6 (nx <= 198)
-// read the 8 stencil weights of a point from shared memory ([j][k][lane], conflict free).
+// = 43 FP64 instructions per point and stage; the stage is written in three phases whose
+// statements are interleaved across the points of the lane (warp_stage).
 //
 // The block / checkpoint / replay protocol that makes check_f_error (gutsdynamo.f90:450-463)
 // exact is the one described in mag_rk_fast.cuh.
@@ -30,20 +35,19 @@
 namespace magdev {
 
 // Coefficient placement of a variant (MODE):
-//   0  all 15 per-point coefficients in registers                       (PPL = 4)
-//   1  the 8 stencil weights in shared memory, the rest in registers    (PPL = 5)
-//   2  stencil weights and p3, qc in shared memory                      (PPL = 6)
+//   0  all 15 per-point coefficients in registers                       (not used by default)
+//   1  the 8 stencil weights in shared memory, the rest in registers    (PPL = 4, 5: nx <= 160)
+//   2  stencil weights and p3, qc in shared memory                      (PPL = 6: nx <= 192)
 //   3  everything streamed from a pair table in the team workspace (global memory, L1/L2
-//      resident), only f and ftmp in registers                          (PPL = 8, 11)
+//      resident), only f and ftmp in registers                          (PPL = 8, 11: nx <= 352)
 // Pair tables are double2 [j*NQ + q][lane]: one conflict-free / coalesced 128-bit load per
 // pair.  q = 0..3: (w0,w1) (w2,w3) (w4,w5) (w6,w0a); shared-memory tables add q = 4: (p3,qc);
 // the global table adds q = 4..7: (ca,gs) (c0,fk) (ak,p3) (qc,-).
 // The loads are volatile asm so that the compiler cannot hoist them out of the time loop (the
 // table is loop invariant; hoisting would put it back into registers and spill).
-// Up to which PPL the three stages of a step are unrolled.  Unrolled loops are ~40 % faster
-// when every warp of an SM runs the same variant, but eight warps running eight different
-// 15-20 KB loops thrash the instruction caches (ncu: stall_no_instruction 15 cycles per
-// issue on the synthetic catalogue), so the default is the looped body.
+// Build-time experiments (see the header): MAG_WARP_UNROLL_MAXPPL unrolls the three stages up
+// to that PPL, MAG_WARP_SPECIALIZE_DEFAULT adds an unrolled instantiation with a compile-time
+// outer alignment for the default grid (nx = 107).  Both lose on the mixed catalogue.
 #ifndef MAG_W4_MODE
 #define MAG_W4_MODE WM_WSM   // same speed as WM_REGS on the looped body, smaller code, no spills
 #endif

@@ -505,10 +505,24 @@ int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t 
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t nr = c->P.p_nx_ref;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  // Output arrays in pinned (mapped) host memory are written by the kernels directly: every row
+  // is written once, by one warp, as contiguous 8-byte stores, so the transfer overlaps the
+  // solve instead of following it.  Pageable buffers are staged in HBM and copied afterwards.
+  auto mapped = [](const void* h) -> void* {
+    if (!h) return nullptr;
+    const char* env = getenv("MAG_ZERO_COPY");
+    if (env && env[0] == '0') return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  void* const m_prof = mapped(out->profiles);
+  void* const m_scal = mapped(out->scalars);
+  void* const m_stat = mapped(out->status);
   const size_t b_in = al(sizeof(double) * MAG_NINPUT * ngal * nz), b_t = al(sizeof(double) * nz), b_id = al(sizeof(int32_t) * ngal);
-  const size_t b_prof = out->profiles ? al(sizeof(double) * n_profile_q * ngal * nz * nr) : 0;
-  const size_t b_scal = out->scalars ? al(sizeof(double) * n_scalar_q * ngal * nz) : 0;
-  const size_t b_stat = out->status ? al((size_t)ngal * nz) : 0;
+  const size_t b_prof = (out->profiles && !m_prof) ? al(sizeof(double) * n_profile_q * ngal * nz * nr) : 0;
+  const size_t b_scal = (out->scalars && !m_scal) ? al(sizeof(double) * n_scalar_q * ngal * nz) : 0;
+  const size_t b_stat = (out->status && !m_stat) ? al((size_t)ngal * nz) : 0;
   const size_t b_i32 = al(sizeof(int32_t) * ngal), b_i64 = al(sizeof(int64_t) * ngal);
   const size_t total = b_in + b_t + b_id + b_prof + b_scal + b_stat + 3 * b_i32 + b_i64;
   if (total > c->stage_bytes) {
@@ -521,9 +535,9 @@ int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t 
   double* d_t = (double*)p; p += b_t;
   int32_t* d_id = (int32_t*)p; p += b_id;
   mag_outputs_t d;
-  d.profiles = out->profiles ? (double*)p : nullptr; p += b_prof;
-  d.scalars = out->scalars ? (double*)p : nullptr; p += b_scal;
-  d.status = out->status ? (char*)p : nullptr; p += b_stat;
+  d.profiles = out->profiles ? (m_prof ? (double*)m_prof : (double*)p) : nullptr; p += b_prof;
+  d.scalars = out->scalars ? (m_scal ? (double*)m_scal : (double*)p) : nullptr; p += b_scal;
+  d.status = out->status ? (m_stat ? (char*)m_stat : (char*)p) : nullptr; p += b_stat;
   d.nsteps = (int32_t*)p; p += b_i32;
   d.error = (int32_t*)p; p += b_i32;
   d.flags = (uint32_t*)p; p += b_i32;
@@ -537,9 +551,9 @@ int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t 
   int rc = launch_solve(c, ngal, d_id, nz, d_t, d_in, n_profile_q, profile_q, n_scalar_q, scalar_q, &d, st);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(c->ev[2], st));
-  if (out->profiles) CUDA_TRY(cudaMemcpyAsync(out->profiles, d.profiles, sizeof(double) * n_profile_q * ngal * nz * nr, cudaMemcpyDeviceToHost, st));
-  if (out->scalars) CUDA_TRY(cudaMemcpyAsync(out->scalars, d.scalars, sizeof(double) * n_scalar_q * ngal * nz, cudaMemcpyDeviceToHost, st));
-  if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)ngal * nz, cudaMemcpyDeviceToHost, st));
+  if (out->profiles && !m_prof) CUDA_TRY(cudaMemcpyAsync(out->profiles, d.profiles, sizeof(double) * n_profile_q * ngal * nz * nr, cudaMemcpyDeviceToHost, st));
+  if (out->scalars && !m_scal) CUDA_TRY(cudaMemcpyAsync(out->scalars, d.scalars, sizeof(double) * n_scalar_q * ngal * nz, cudaMemcpyDeviceToHost, st));
+  if (out->status && !m_stat) CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)ngal * nz, cudaMemcpyDeviceToHost, st));
   if (out->nsteps) CUDA_TRY(cudaMemcpyAsync(out->nsteps, d.nsteps, sizeof(int32_t) * ngal, cudaMemcpyDeviceToHost, st));
   if (out->error) CUDA_TRY(cudaMemcpyAsync(out->error, d.error, sizeof(int32_t) * ngal, cudaMemcpyDeviceToHost, st));
   if (out->flags) CUDA_TRY(cudaMemcpyAsync(out->flags, d.flags, sizeof(uint32_t) * ngal, cudaMemcpyDeviceToHost, st));

@@ -244,3 +244,42 @@ def test_fine_grid_config5(oracle, example_input):
     ora = oracle.solve_batch(p, ids, t, sub, nthreads=3)
     rep = compare(gpu, ora)
     print("config 5 worst errors:", {k: f"{v:.1e}" for k, v in rep.items() if v > 0}, info)
+
+
+def test_pinned_outputs_are_written_in_place(solver, example_input):
+    """mag_solve_batch writes rows straight into pinned (mapped) host buffers instead of staging
+    them in HBM; the result is identical to the staged path with pageable buffers."""
+    t, inputs = example_input
+    ids, sub = _subset(inputs, [1, 5, 24, 30, 60, 101, 150])
+    prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax",)
+    staged = solver.run(ids, t, sub, profiles=prof, scalars=scal)
+    out = solver.alloc_outputs(len(ids), t.size, prof, scal, pinned=True)
+    mapped = solver.run(ids, t, sub, profiles=prof, scalars=scal, out=out)
+    for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"):
+        assert np.array_equal(np.asarray(staged[k]), np.asarray(mapped[k]), equal_nan=(k in ("profiles", "scalars"))), k
+
+
+def test_warp_path_every_alignment_matches_generic_path(example_input):
+    """The one-warp fast path places the outer Dirichlet point in register (nx-4) % PPL of its
+    lane and switches at run time on that position; p_nx_ref = 95..135 walks through every
+    position of the 4-, 5- and 6-register variants (and grid growth inside the histories
+    reaches the 8-register one).  Fast path and any-nx generic path must agree to rounding."""
+    from magnetizer_b200.solver import DynamoSolver, default_params
+    t, inputs = example_input
+    ids, sub = _subset(inputs, [24, 101])
+    prof, scal = ("Br", "Bp", "alp_m", "alp", "Bzmod"), ("Bmax", "Bmax_idx")
+    for nref in list(range(95, 107)) + [121, 122, 123, 124, 125, 131, 135, 150, 163]:
+        p = default_params()
+        p.p_nx_ref = nref
+        s = DynamoSolver(params=p, device=0)
+        try:
+            fast = s.run(ids, t, sub, profiles=prof, scalars=scal)
+            assert s.info()["fast_path_replays"] == 0
+            s.set_fast_path(False)
+            slow = s.run(ids, t, sub, profiles=prof, scalars=scal)
+        finally:
+            s.close()
+        assert fast["status"].tobytes() == slow["status"].tobytes(), nref
+        assert np.array_equal(fast["nsteps"], slow["nsteps"]), nref
+        rep = compare(fast, slow)
+        assert max(rep.values()) < 1e-8, (nref, rep)
