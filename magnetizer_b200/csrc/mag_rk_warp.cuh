@@ -340,10 +340,17 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
   for (int j = 0; j < PPL; j++) {
     S.f[0][j] = fma(dg, p0[j], S.ft[0][j]); S.f[1][j] = fma(dg, p1[j], S.ft[1][j]); S.f[2][j] = fma(dg, p2[j], S.ft[2][j]);
   }
+  // the new state is final: the halo exchange for the next stage starts now; its 36 shuffles
+  // (one issue slot every ~4 cycles) are interleaved with the ftmp update and the maxima
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
-    if (LAST) { S.ft[0][j] = S.f[0][j]; S.ft[1][j] = S.f[1][j]; S.ft[2][j] = S.f[2][j]; }
-    else { S.ft[0][j] = fma(dz, p0[j], S.f[0][j]); S.ft[1][j] = fma(dz, p1[j], S.f[1][j]); S.ft[2][j] = fma(dz, p2[j], S.f[2][j]); }
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+      if (j < 3) S.hr[v][j] = shfl_down1(S.f[v][j]);
+      if (j >= PPL - 3) S.hl[v][j - (PPL - 3)] = shfl_up1(S.f[v][j]);
+      if (LAST) S.ft[v][j] = S.f[v][j];
+      else S.ft[v][j] = fma(dz, v == 0 ? p0[j] : (v == 1 ? p1[j] : p2[j]), S.f[v][j]);
+    }
     // |x| maxima on the high words: signed max catches the positive values, unsigned max the negative ones
     mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(S.f[0][j]), __double2hiint(S.f[1][j]));
     mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(S.f[0][j]), (unsigned)__double2hiint(S.f[1][j]));
@@ -526,19 +533,15 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
       const bool last_step = jt + s == nsteps;
       if (JM >= 0 || PPL <= MAG_WARP_UNROLL_MAXPPL) {  // three stages unrolled: their shuffles and chains overlap
         warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg0, dz0, mBs, mBu, mAs, mAu);
-        warp_exchange<PPL, MODE>(S);
         warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg1, dz1, mBs, mBu, mAs, mAu);
-        warp_exchange<PPL, MODE>(S);
         if (last_step) save_alp();
         warp_stage<PPL, MODE, JM, true>(S, wsa, tab, lane, tm, jm, dg2, 0.0, mBs, mBu, mAs, mAu);
-        warp_exchange<PPL, MODE>(S);
       } else {         // one stage body, looped: a three times smaller instruction footprint
 #pragma unroll 1
         for (int st = 0; st < 3; st++) {
           const double dg = rs->stage_dg[st], dz = rs->stage_dz[st];
           if (st == 2 && last_step) save_alp();
           warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg, dz, mBs, mBu, mAs, mAu);
-          warp_exchange<PPL, MODE>(S);
           if (PPL > WARP_LATE_GHOSTS_MAXPPL) warp_ghosts<PPL, MODE, JM>(S, lane, tm, jm);
         }
       }
