@@ -286,7 +286,7 @@ def main():
     ap.add_argument("--ngal", type=int, default=int(os.environ.get("MAG_BENCH_NGAL", "40000")),
                     help="galaxies per GPU per step (weak scaling).  The workload is BASELINE config 3's synthetic "
                          "catalogue; the default batch is large enough that the longest history (800 000 RK steps, "
-                         "~2 s on one 64-thread team) does not set the step time")
+                         "~1.8 s on its warp) does not set the step time")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

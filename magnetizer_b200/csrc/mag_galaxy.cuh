@@ -107,6 +107,8 @@ struct Gal {
   // hydrostatic chain handling (mag_phases.cuh): inline / export jobs / import results
   int chain_mode, chain_it, chain_kind, chain_job;
   bool chain_diverged;
+  // first / last snapshot whose output rows this phase has written (fill_unwritten)
+  int w0, w1;
   // status / stats
   char status;
   uint32_t flags;
@@ -935,6 +937,7 @@ __device__ inline void write_profile_rows(Gal& G, int it) {
   const KernelArgs* a = G.a;
   const int nr = a->P.p_nx_ref, ni = G.nx - 2 * MAG_NGHOST, ng = MAG_NGHOST, lane = G.lane;
   const int nz = a->nz, ngal = a->ngal, g = G.g;
+  G.w0 = min(G.w0, it); G.w1 = max(G.w1, it);
   if (a->out.profiles) {
     for (int qq = 0; qq < a->n_profile_q; qq++) {
       const int q = a->profile_q[qq];
@@ -955,6 +958,7 @@ __device__ inline void write_field_rows(Gal& G, int it) {
   const int nr = a->P.p_nx_ref, ni = G.nx - 2 * MAG_NGHOST, ng = MAG_NGHOST, lane = G.lane;
   const int nz = a->nz, ngal = a->ngal, g = G.g;
   const bool alp_ok = (G.status == 'M' || G.status == 'm');
+  G.w0 = min(G.w0, it); G.w1 = max(G.w1, it);
   if (a->out.status && lane == 0) a->out.status[(size_t)g * nz + it - 1] = G.status;
   if (a->out.profiles) {
     for (int qq = 0; qq < a->n_profile_q; qq++) {
@@ -1018,6 +1022,36 @@ __device__ inline void reset_outputs(const Gal& G) {
   // processes (ts_arrays.f90:99-121), an order dependence that is not reproduced
   if (a->out.status)
     for (int i = lane; i < nz; i += 32) a->out.status[(size_t)g * nz + i] = '-';
+}
+
+
+// "Never written" markers for the rows a phase owns and did not write: snapshots outside
+// [G.w0, G.w1] (a phase writes a contiguous range of snapshots).  field_part: Br, Bp, alp_m,
+// Bzmod, alp, the scalars and the status (evolve phase); otherwise the ISM-profile rows
+// (profile phase).  Every output row is thus stored exactly once -- this matters when the
+// outputs live in mapped host memory and every store crosses PCIe.
+__device__ inline void fill_unwritten(const Gal& G, bool field_part) {
+  const KernelArgs* a = G.a;
+  const int nr = a->P.p_nx_ref, nz = a->nz, ngal = a->ngal, g = G.g, lane = G.lane;
+  const int w0 = G.w1 >= G.w0 ? G.w0 : nz + 1, w1 = G.w1 >= G.w0 ? G.w1 : nz;   // nothing written: everything is "before"
+  for (int part = 0; part < 2; part++) {
+    const int s0 = part == 0 ? 1 : w1 + 1, s1 = part == 0 ? w0 - 1 : nz;   // snapshots s0..s1 (1-based)
+    if (s1 < s0) continue;
+    if (a->out.profiles)
+      for (int qq = 0; qq < a->n_profile_q; qq++) {
+        if (is_field_quantity(a->profile_q[qq]) != field_part) continue;
+        double* dst = a->out.profiles + (((size_t)qq * ngal + g) * nz + (s0 - 1)) * nr;
+        for (int i = lane; i < (s1 - s0 + 1) * nr; i += 32) dst[i] = MAG_INVALID;
+      }
+    if (field_part) {
+      if (a->out.scalars)
+        for (int qq = 0; qq < a->n_scalar_q; qq++)
+          for (int i = s0 - 1 + lane; i < s1; i += 32) a->out.scalars[((size_t)qq * ngal + g) * nz + i] = MAG_INVALID;
+      if (a->out.status)
+        for (int i = s0 - 1 + lane; i < s1; i += 32) a->out.status[(size_t)g * nz + i] = '-';
+    }
+  }
+  __syncwarp();
 }
 
 }  // namespace magdev

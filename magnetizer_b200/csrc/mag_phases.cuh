@@ -184,7 +184,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
   G.t = 0; G.dt = 0; G.nsteps = 20; G.time_between_inputs = 0; G.minh = 1e10; G.maxetat = 0; G.tau_min = 0;
   G.t_last_sign_choice = 0; G.refresh_sign = true; G.sign_nx = -1;
   H.cost = 0; H.flags = 0; H.error = 0;
-  if (!exporting) reset_outputs(G);
+  G.w0 = G.a->nz + 1; G.w1 = 0;   // no output row written yet (k_profiles fills the rest afterwards)
   load_input_parameters(G);
   H.init_it = G.init_it; H.max_it = G.max_it;
   if (set_input_params(G)) return true;
@@ -312,6 +312,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
   G.sign_nx = -1;
   G.flags = H.flags; G.point_stages = 0;
   G.t = 0; G.nsteps = 20;
+  G.w0 = a->nz + 1; G.w1 = 0;
   G.init_it = H.init_it; G.max_it = H.max_it;
   const SnapRec* recs = a->recs + (size_t)G.g * a->nz;
   G.nx = recs[H.init_it - 1].nx;
@@ -393,6 +394,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
     PHASE_END(2, lane);
     if (last) break;
   }
+  fill_unwritten(G, true);
   if (lane == 0) {
     if (a->out.nsteps) a->out.nsteps[G.g] = G.nsteps;
     if (a->out.point_stages) a->out.point_stages[G.g] = G.point_stages;

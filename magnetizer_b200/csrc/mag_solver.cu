@@ -63,6 +63,11 @@ __global__ void __maxnreg__(MAG_PROFILE_MAXREG) k_profiles(KernelArgs a) {
     const bool err = run_profiles(G, H);
     H.error = err ? 1 : 0;
     if (err) H.cost = 0;
+    if (a.chain_mode != CHAIN_MODE_EXPORT) {
+      // rows nobody will write: everything for a galaxy the evolve phase skips (dynamo.f90:69-73),
+      // else the ISM-profile rows outside the snapshots processed above
+      if (err) reset_outputs(G); else fill_unwritten(G, false);
+    }
     if (lane == 0 && a.chain_mode != CHAIN_MODE_EXPORT) {
       a.heads[q] = H;
       if (a.out.error) a.out.error[G.g] = H.error;
