@@ -13,8 +13,9 @@
 //
 // Input: the reference's HDF5 input file (own minimal reader).  Output: the reference's
 // dataset names and shapes (Output/<q> [ngal][nx][nz], scalars [ngal][nz], Log/status ...),
-// stored as an uncompressed .npz container (readable with numpy.load); the native HDF5
-// writer is SURVEY.md row 8(f1), not part of this round.
+// written either as an HDF5 file in the reference's layout (mag_hdf5_writer.hpp: /Output, /Log,
+// units/description attributes, the namelists as root attributes; the default) or, when the
+// output name ends in .npz, as an uncompressed .npz container (readable with numpy.load).
 //
 //   Magnetizer_b200 <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.npz]
 #include <chrono>
@@ -23,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -31,6 +33,7 @@
 
 #include "../../include/magnetizer_b200.h"
 #include "mag_hdf5_reader.hpp"
+#include "mag_hdf5_writer.hpp"
 #include "mag_namelist.hpp"
 
 namespace {
@@ -49,6 +52,39 @@ double unit_factor(const std::string& q) {
   if (q == "n") return n0_cm3;
   return 1.0;
 }
+
+// 'Units' and 'Description' attributes of write_output (output.f90:37-201)
+struct QuantityDoc { const char *name, *units, *description; };
+const QuantityDoc kQuantityDocs[] = {
+    {"r", "kpc", "Radius"}, {"rkpc", "kpc", "Radius"}, {"Br", "microgauss", ""}, {"Bp", "microgauss", ""}, {"alp_m", "km/s", ""},
+    {"Bzmod", "microgauss", ""}, {"h", "pc", "Disk scaleheight"}, {"Omega", "km/s/kpc", "Angular velocity"},
+    {"Shear", "km/s/kpc", "Shear"}, {"l", "pc", "Turbulent length"}, {"v", "km/s", "Turbulent velocity"},
+    {"etat", "kpc km/s", ""}, {"tau", "", ""}, {"alp_k", "km/s", ""}, {"Uz", "km/s", "Vertical velocity (outflow)"},
+    {"n", "cm^-3", "Number density of diffuse gas"}, {"Beq", "microgauss", "Equipartition field"},
+    {"rmax", "kpc", "Radius of maximum |B|"}, {"Bmax", "microgauss", "Maximum B"}, {"Bmax_idx", "", "Index of maximum |B|"},
+    {"alp", "km/s", ""}, {"dt", "", ""}, {"Omega_h", "km/s/kpc", "Angular velocity of the halo"},
+    {"Omega_b", "km/s/kpc", "Angular velocity of the bulge"}, {"Omega_d", "km/s/kpc", "Angular velocity of the disc"},
+    {"Bavg", "microgauss", "Surface average magnetic field"}, {"Beavg", "microgauss", "\"Energy averaged\" magnetic field"},
+    {"runtime", "s", "Running time of the galaxy"}, {"nsteps", "", "Number of timesteps"}, {"status", "", "Status codes."}};
+maghost::Hdf5Writer::TextAttrs quantity_attrs(const std::string& q) {
+  maghost::Hdf5Writer::TextAttrs a;
+  for (const auto& d : kQuantityDocs)
+    if (q == d.name) {
+      if (d.units[0]) a.push_back({"Units", d.units});
+      if (d.description[0]) a.push_back({"Description", d.description});
+    }
+  return a;
+}
+
+// One output sink for both containers: HDF5 (reference layout) or .npz
+struct OutputFile {
+  std::unique_ptr<maghost::Hdf5Writer> h5;
+  std::unique_ptr<struct NpzWriter> npz;
+  void add_f64(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const double* data);
+  void add_status(const std::vector<size_t>& shape, const char* data);
+  void add_i32(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const int32_t* data);
+  void close();
+};
 
 // ---- uncompressed .npz (zip of .npy files, "stored" method)
 struct NpzWriter {
@@ -100,6 +136,76 @@ struct NpzWriter {
     f = nullptr;
   }
 };
+
+void OutputFile::add_f64(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const double* data) {
+  size_t n = 1;
+  for (size_t d : shape) n *= d;
+  if (h5) h5->add_dataset(group, name, maghost::Hdf5Writer::F64, std::vector<uint64_t>(shape.begin(), shape.end()), data, quantity_attrs(name));
+  else npz->add(group + "/" + name, "<f8", shape, data, n * 8);
+}
+void OutputFile::add_status(const std::vector<size_t>& shape, const char* data) {
+  if (h5) h5->add_dataset("Log", "status", maghost::Hdf5Writer::CHAR1, std::vector<uint64_t>(shape.begin(), shape.end()), data, quantity_attrs("status"));
+  else npz->add("Log/status", "|S1", shape, data, shape[0] * shape[1]);
+}
+void OutputFile::add_i32(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const int32_t* data) {
+  size_t n = 1;
+  for (size_t d : shape) n *= d;
+  if (h5) h5->add_dataset(group, name, maghost::Hdf5Writer::I32, std::vector<uint64_t>(shape.begin(), shape.end()), data);
+  else npz->add(group + "/" + name, "<i4", shape, data, n * 4);
+}
+void OutputFile::close() {
+  if (h5) h5->close();
+  if (npz) npz->close();
+}
+
+// the namelists as gfortran prints them into one record (IO_hdf5.f90:191-216; parsed by
+// python/magnetizer/parameters.py): "&NAME  KEY=value, KEY=value, /"
+std::string nml_text(const char* name, const std::vector<std::pair<std::string, std::string>>& kv) {
+  std::string s = std::string("&") + name + " ";
+  for (const auto& p : kv) {
+    std::string k = p.first;
+    for (auto& c : k) c = (char)std::toupper((unsigned char)c);
+    s += " " + k + "=" + p.second + ",";
+  }
+  return s + " /";
+}
+std::string fnum(double v) { char b[40]; std::snprintf(b, sizeof b, "%.17g", v); return b; }
+std::string fint(long v) { return std::to_string(v); }
+std::string fbool(int v) { return v ? "T" : "F"; }
+
+void write_parameter_attributes(maghost::Hdf5Writer& w, const maghost::RunConfig& cfg) {
+  const mag_params_t& p = cfg.params;
+  w.add_root_attribute("Model name", cfg.model_name);
+  w.add_root_attribute("run_parameters", nml_text("RUN_PARAMETERS", {{"model_name", "\"" + cfg.model_name + "\""}, {"info", fint(cfg.info)},
+      {"nsteps_0", fint(p.nsteps_0)}, {"p_courant_v", fnum(p.p_courant_v)}, {"p_courant_eta", fnum(p.p_courant_eta)},
+      {"p_variable_timesteps", fbool(p.p_variable_timesteps)}, {"p_nsteps_max", fint(p.p_nsteps_max)},
+      {"p_no_magnetic_fields_test_run", fbool(p.p_no_magnetic_fields_test_run)}, {"p_MAX_FAILS", fint(p.p_MAX_FAILS)},
+      {"p_random_seed", fint(p.p_random_seed)}}));
+  w.add_root_attribute("io_parameters", nml_text("IO_PARAMETERS", {{"output_file_name", "\"" + cfg.output_file_name + "\""},
+      {"input_file_name", "\"" + cfg.input_file_name + "\""}, {"p_IO_separate_output", "T"}, {"p_IO_chunking", "F"}, {"p_IO_compression", "F"}}));
+  w.add_root_attribute("grid_parameters", nml_text("GRID_PARAMETERS", {{"p_nx_ref", fint(p.p_nx_ref)}, {"p_nx_MAX", fint(p.p_nx_MAX)},
+      {"p_rmax_over_rdisk", fnum(p.p_rmax_over_rdisk)}}));
+  w.add_root_attribute("dynamo_parameters", nml_text("DYNAMO_PARAMETERS", {{"Dyn_quench", fbool(p.Dyn_quench)}, {"Alg_quench", fbool(p.Alg_quench)},
+      {"lFloor", fbool(p.lFloor)}, {"Damp", fbool(p.Damp)}, {"frac_seed", fnum(p.frac_seed)}, {"p_seed_choice", "\"random\""},
+      {"C_alp", fnum(p.C_alp)}, {"C_floor", fnum(p.C_floor)}, {"p_floor_kappa", fnum(p.p_floor_kappa)},
+      {"p_space_varying_floor", fbool(p.p_space_varying_floor)}, {"p_time_varying_floor", fbool(p.p_time_varying_floor)},
+      {"fmag", fnum(p.fmag)}, {"R_kappa", fnum(p.R_kappa)}}));
+  w.add_root_attribute("ISM_and_disk_parameters", nml_text("ISM_AND_DISK_PARAMETERS", {
+      {"p_ISM_sound_speed_km_s", fnum(p.p_ISM_sound_speed_km_s)}, {"p_ISM_kappa", fnum(p.p_ISM_kappa)}, {"p_ISM_xi", fnum(p.p_ISM_xi)},
+      {"p_ISM_gamma", fnum(p.p_ISM_gamma)}, {"p_ISM_turbulent_length", fnum(p.p_ISM_turbulent_length)},
+      {"p_limit_turbulent_scale", fbool(p.p_limit_turbulent_scale)},
+      {"p_stellarHeightToRadiusScale", fnum(p.p_stellarHeightToRadiusScale)},
+      {"p_molecularHeightToRadiusScale", fnum(p.p_molecularHeightToRadiusScale)},
+      {"p_gasScaleRadiusToStellarScaleRadius_ratio", fnum(p.p_gasScaleRadiusToStellarScaleRadius_ratio)},
+      {"p_Rmol_alpha", fnum(p.p_Rmol_alpha)}, {"p_Rmol_P0", fnum(p.p_Rmol_P0)},
+      {"p_allow_positive_shears", fbool(p.p_allow_positive_shears)}, {"p_simplified_pressure", fbool(p.p_simplified_pressure)},
+      {"p_rreg_to_rdisk", fnum(p.p_rreg_to_rdisk)}, {"p_rdisk_min", fnum(p.p_rdisk_min)}, {"Mgas_disk_min", fnum(p.Mgas_disk_min)},
+      {"rmin_over_rmax", fnum(p.rmin_over_rmax)}, {"p_ignore_satellite_DM_haloes", fbool(p.p_ignore_satellite_DM_haloes)},
+      {"p_enable_P2", fbool(p.p_enable_P2)}, {"p_minimum_density", fnum(p.p_minimum_density)}, {"p_use_Pdm", fbool(p.p_use_Pdm)},
+      {"p_use_Pbulge", fbool(p.p_use_Pbulge)}, {"p_halo_contraction", fbool(p.p_halo_contraction)}}));
+  w.add_root_attribute("outflow_parameters", nml_text("OUTFLOW_PARAMETERS", {{"p_outflow_type", "\"no_outflow\""}}));
+  w.add_root_attribute("File creation", "magnetizer_b200 host driver");
+}
 
 }  // namespace
 
@@ -181,13 +287,18 @@ int main(int argc, char** argv) {
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
     // ---- write_output (output.f90:23-236): unit conversion, [ngal][nx][nz] layout, Log group
-    if (out_path.empty()) {
-      out_path = cfg.output_file_name.empty() ? "magnetizer_b200_output.npz" : cfg.output_file_name;
-      const size_t dot = out_path.rfind('.');
-      out_path = (dot == std::string::npos ? out_path : out_path.substr(0, dot)) + ".npz";
+    if (out_path.empty()) out_path = cfg.output_file_name.empty() ? "magnetizer_b200_output.hdf5" : cfg.output_file_name;
+    const bool as_npz = out_path.size() > 4 && out_path.compare(out_path.size() - 4, 4, ".npz") == 0;
+    OutputFile w;
+    if (as_npz) {
+      w.npz.reset(new NpzWriter(out_path));
+      if (!w.npz->ok()) throw std::runtime_error("cannot write " + out_path);
+    } else {
+      w.h5.reset(new maghost::Hdf5Writer(out_path));
+      w.h5->add_group("Output");
+      w.h5->add_group("Log");
+      write_parameter_attributes(*w.h5, cfg);
     }
-    NpzWriter w(out_path);
-    if (!w.ok()) throw std::runtime_error("cannot write " + out_path);
     std::vector<double> tmp((size_t)ngal * nr * nz);
     long long total_stages = 0;
     for (auto s : stages) total_stages += s;
@@ -201,12 +312,12 @@ int main(int argc, char** argv) {
             const double v = src[((size_t)g * nz + iz) * nr + i];
             tmp[((size_t)g * nr + i) * nz + iz] = (v == MAG_INVALID) ? v : v * fac;
           }
-      if (name != "rkpc" || have_rkpc) w.add("Output/" + name, "<f8", {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data(), tmp.size() * 8);
-      if (name == "rkpc") w.add("Output/r", "<f8", {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data(), tmp.size() * 8);
+      if (name != "rkpc" || have_rkpc) w.add_f64("Output", name, {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data());
+      if (name == "rkpc") w.add_f64("Output", "r", {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data());
     }
     for (size_t q = 0; q < sq.size(); q++)
-      w.add(std::string("Output/") + kScalarNames[sq[q]], "<f8", {(size_t)ngal, (size_t)nz}, &scalars[q * (size_t)ngal * nz], (size_t)ngal * nz * 8);
-    w.add("Log/status", "|S1", {(size_t)ngal, (size_t)nz}, status.data(), status.size());
+      w.add_f64("Output", kScalarNames[sq[q]], {(size_t)ngal, (size_t)nz}, &scalars[q * (size_t)ngal * nz]);
+    w.add_status({(size_t)ngal, (size_t)nz}, status.data());
     std::vector<double> log_n(ngal), log_c(ngal), log_rt(ngal);
     std::map<char, long> counts;
     for (int g = 0; g < ngal; g++) {
@@ -215,11 +326,13 @@ int main(int argc, char** argv) {
       log_rt[g] = total_stages > 0 ? secs * (double)stages[g] / (double)total_stages : 0.0;
       for (int iz = 0; iz < nz; iz++) counts[status[(size_t)g * nz + iz]]++;
     }
-    w.add("Log/nsteps", "<f8", {(size_t)ngal}, log_n.data(), log_n.size() * 8);
-    w.add("Log/completed", "<f8", {(size_t)ngal}, log_c.data(), log_c.size() * 8);
-    w.add("Log/runtime", "<f8", {(size_t)ngal}, log_rt.data(), log_rt.size() * 8);
-    w.add("Log/gal_id", "<i4", {(size_t)ngal}, list.data(), list.size() * 4);
-    w.add("Input/t", "<f8", {(size_t)nz}, in.t_gyr.data(), in.t_gyr.size() * 8);
+    // Log datasets are (ngals, 1) in the reference's file (Fortran (1, ngals), output.f90:37-54)
+    const std::vector<size_t> log_shape = as_npz ? std::vector<size_t>{(size_t)ngal} : std::vector<size_t>{(size_t)ngal, 1};
+    w.add_f64("Log", "nsteps", log_shape, log_n.data());
+    w.add_f64("Log", "completed", log_shape, log_c.data());
+    w.add_f64("Log", "runtime", log_shape, log_rt.data());
+    w.add_i32("Log", "gal_id", {(size_t)ngal}, list.data());
+    if (as_npz) w.add_f64("Input", "t", {(size_t)nz}, in.t_gyr.data());
     w.close();
     std::printf("  solved in %.3f s  (%.1f galaxies/s, %.3e point-stages/s)\n", secs, ngal / secs, total_stages / secs);
     for (size_t d = 0; d < devices.size(); d++)

@@ -74,8 +74,17 @@ def test_driver_end_to_end_example(exe, oracle, example_input, tmp_path):
         assert np.all(np.abs(got - want) <= RTOL * np.maximum(scale, 1e-300)), name
     assert np.array_equal(d["Log/status"].view("S1").reshape(196, 40), ora["status"])
     assert np.array_equal(d["Log/nsteps"], ora["nsteps"].astype(float))
-    # single-galaxy mode (Fortran gal_id = 1)
-    out1 = str(tmp_path / "example_output_gal1.npz")
+    # single-galaxy mode (Fortran gal_id = 1), written as HDF5 in the reference's layout
+    # (mag_hdf5_writer.hpp) and read back with the pure-python reader
+    from magnetizer_b200.hdf5_min import H5File
+    out1 = str(tmp_path / "example_output_gal1.hdf5")
     subprocess.check_call([exe, PARAMS, "1", "--out", out1], cwd=ROOT, stdout=subprocess.DEVNULL)
-    d1 = np.load(out1)
-    assert np.array_equal(d1["Output/Br"][0], d["Output/Br"][0]) and d1["Log/gal_id"].tolist() == [1]
+    f1 = H5File(out1)
+    assert f1.keys("/") == ["Log", "Output"] and "Br" in f1.keys("Output") and "r" in f1.keys("Output")
+    assert np.array_equal(f1["Output/Br"][0], d["Output/Br"][0]) and f1["Log/gal_id"].tolist() == [1]
+    assert f1["Output/Br"].shape == (1, 101, 40) and f1["Log/status"].shape == (1, 40) and f1["Log/nsteps"].shape == (1, 1)
+    assert f1["Log/status"].tobytes() == ora["status"][0].tobytes()
+    assert f1.attrs("Output/Br")["Units"] == "microgauss" and f1.attrs("Output/h")["Description"] == "Disk scaleheight"
+    root = f1.attrs("/")
+    assert "P_NX_REF=101," in root["grid_parameters"] and root["run_parameters"].startswith("&RUN_PARAMETERS ")
+    assert float(re.search(r"P_COURANT_V=([^,]+),", root["run_parameters"])[1]) == 0.09000000357627869
