@@ -1,5 +1,6 @@
-"""Phase clocks of the evolve kernel (GPU box, debug build with -DMAG_PHASE_CLOCKS as
-magnetizer_b200/libmag_clk.so): where lane 0 of the evolve teams spends its cycles."""
+"""Phase clocks of the evolve kernel (GPU box; debug build with -DMAG_PHASE_CLOCKS:
+`make -C magnetizer_b200/csrc clk` -> magnetizer_b200/libmag_clk.so): where lane 0 of the
+evolve teams spends its cycles."""
 import ctypes as C
 import os
 import sys
