@@ -210,7 +210,12 @@ void mag_destroy(mag_ctx_t *ctx);
  *  profile_q[n_profile_q], scalar_q[n_scalar_q]  requested quantities
  *  out                          HOST buffers
  *
- * Host<->device copies happen inside the call.
+ * Host<->device copies happen inside the call.  If out->profiles / scalars / status are
+ * pinned (page-locked, mapped) host memory -- cudaHostAlloc, cudaHostRegister, or e.g.
+ * torch pin_memory() -- the kernels store the rows directly into them while the solve runs
+ * (every row is stored exactly once) and no staging copy follows; pageable arrays, such as
+ * the Fortran allocatables of the reference's modules, are staged in HBM and copied after
+ * the solve.  MAG_ZERO_COPY=0 in the environment forces the staged path.
  */
 int mag_solve_batch(mag_ctx_t *ctx, int32_t ngal, const int32_t *gal_ids, int32_t nz,
                     const double *t_gyr, const double *inputs,
