@@ -20,6 +20,14 @@
 #include "mag_bessel_coeffs.cuh"
 
 #define DET_FN __device__ __forceinline__
+// log, exp and the Bessel series are inlined ~45 / ~36 / ~10 times into k_profiles (770 KB of
+// code, instruction-cache bound: DESIGN.md section 7).  -DMAG_DET_NOINLINE builds them out of line
+// (same arithmetic; an experiment for the next round, default off).
+#ifdef MAG_DET_NOINLINE
+#define DET_BIG __device__ __noinline__
+#else
+#define DET_BIG __device__ __forceinline__
+#endif
 
 namespace detmath {
 
@@ -31,7 +39,7 @@ DET_FN double det_inf() { return __hiloint2double(0x7ff00000, 0); }
 
 // ==== BEGIN TWIN (identical text in oracle/det_math.hpp) ====
 // natural logarithm, x > 0 finite (0 -> -inf, negative -> NaN)
-DET_FN double det_log(double x) {
+DET_BIG double det_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
   const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01;
   const double Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01;
@@ -81,7 +89,7 @@ DET_FN double det_log(double x) {
 }
 
 // exponential
-DET_FN double det_exp(double x) {
+DET_BIG double det_exp(double x) {
   const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10;
   const double invln2 = 1.44269504088896338700e+00;
   const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05;
@@ -141,7 +149,7 @@ DET_FN double det_cheb(const double* c, int n, double t) {
 }
 
 // modified Bessel functions I0, I1, K0, K1 of x > 0, all four at once
-DET_FN void det_bessel_ik01(double x, double* i0, double* i1, double* k0, double* k1) {
+DET_BIG void det_bessel_ik01(double x, double* i0, double* i1, double* k0, double* k1) {
   const double euler = 0.57721566490153286061;
   const double q = 0.25 * x * x;
   if (x <= 8.0) {

@@ -30,6 +30,7 @@
 #include "bessel_coeffs.hpp"
 
 #define DET_FN static inline
+#define DET_BIG static inline   /* the large functions; the CUDA twin can build them out of line */
 #define DET_CONST static const
 
 namespace detmath {
@@ -47,7 +48,7 @@ DET_FN double det_inf() { return det_words(0x7ff00000, 0u); }
 
 // ==== BEGIN TWIN (identical text in magnetizer_b200/csrc/mag_det_math.cuh) ====
 // natural logarithm, x > 0 finite (0 -> -inf, negative -> NaN)
-DET_FN double det_log(double x) {
+DET_BIG double det_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
   const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01;
   const double Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01;
@@ -97,7 +98,7 @@ DET_FN double det_log(double x) {
 }
 
 // exponential
-DET_FN double det_exp(double x) {
+DET_BIG double det_exp(double x) {
   const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10;
   const double invln2 = 1.44269504088896338700e+00;
   const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05;
@@ -157,7 +158,7 @@ DET_FN double det_cheb(const double* c, int n, double t) {
 }
 
 // modified Bessel functions I0, I1, K0, K1 of x > 0, all four at once
-DET_FN void det_bessel_ik01(double x, double* i0, double* i1, double* k0, double* k1) {
+DET_BIG void det_bessel_ik01(double x, double* i0, double* i1, double* k0, double* k1) {
   const double euler = 0.57721566490153286061;
   const double q = 0.25 * x * x;
   if (x <= 8.0) {
