@@ -172,6 +172,8 @@ class H5Reader {
       if (n.dt_size == 4) { int32_t v; std::memcpy(&v, p, 4); return n.dt_signed ? (double)v : (double)(uint32_t)v; }
       if (n.dt_size == 2) { int16_t v; std::memcpy(&v, p, 2); return n.dt_signed ? (double)v : (double)(uint16_t)v; }
       if (n.dt_size == 1) return n.dt_signed ? (double)*(const int8_t*)p : (double)*(const uint8_t*)p;
+    } else if (n.dt_class == 3 && n.dt_size == 1) {
+      return (double)*(const uint8_t*)p;   // one-character strings (Log/status): the character code
     }
     throw std::runtime_error("HDF5 datatype not supported");
   }

@@ -211,7 +211,8 @@ void write_parameter_attributes(maghost::Hdf5Writer& w, const maghost::RunConfig
 
 int main(int argc, char** argv) {
   if (argc < 2) {
-    std::fprintf(stderr, "usage: %s <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.npz]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.hdf5|file.npz]\n"
+                         "          [--restart] [--stop-after N] [--dry-run]\n", argv[0]);
     return 2;
   }
   try {
@@ -219,10 +220,13 @@ int main(int argc, char** argv) {
     std::vector<int32_t> list, devices;
     int chunk = 2048;
     std::string out_path;
-    bool dry_run = false;
+    bool dry_run = false, restart = false;
+    long stop_after = -1;
     for (int i = 2; i < argc; i++) {
       const std::string a = argv[i];
       if (a == "--dry-run") { dry_run = true; continue; }
+      if (a == "--restart") { restart = true; continue; }
+      if (a == "--stop-after" && i + 1 < argc) { stop_after = std::atol(argv[++i]); continue; }
       if (a == "--devices" && i + 1 < argc) {
         for (char* tok = std::strtok(argv[++i], ","); tok; tok = std::strtok(nullptr, ",")) devices.push_back(std::atoi(tok));
       } else if (a == "--chunk" && i + 1 < argc) chunk = std::atoi(argv[++i]);
@@ -251,6 +255,30 @@ int main(int argc, char** argv) {
       if (!found) std::fprintf(stderr, "warning: output quantity '%s' is not produced by this path; skipped\n", q.c_str());
     }
     if (!have_rkpc) pq.push_back(MAG_Q_RKPC);  // Output/r is always written (output.f90:56-60)
+    // ---- resume: the output file doubles as checkpoint (distributor.f90:150-156).  Galaxies whose
+    // Log/completed flag is set are not solved again (IO_start_galaxy, IO_hdf5.f90:244-266);
+    // --restart ignores an existing file, --stop-after N ends this invocation after N galaxies
+    // (the graceful stop of the STOP file / p_max_walltime, distributor.f90:299-312).
+    if (out_path.empty()) out_path = cfg.output_file_name.empty() ? "magnetizer_b200_output.hdf5" : cfg.output_file_name;
+    const bool as_npz = out_path.size() > 4 && out_path.compare(out_path.size() - 4, 4, ".npz") == 0;
+    std::unique_ptr<maghost::H5Reader> prev;
+    std::vector<char> completed(ngal, 0);
+    if (!restart && !as_npz) {
+      if (FILE* t = std::fopen(out_path.c_str(), "rb")) {
+        std::fclose(t);
+        prev.reset(new maghost::H5Reader(out_path));
+        const maghost::H5Reader::Data ids = prev->read("Log/gal_id"), comp = prev->read("Log/completed");
+        bool same = ids.v.size() == (size_t)ngal && comp.v.size() == (size_t)ngal;
+        for (int g = 0; same && g < ngal; g++) same = (int32_t)ids.v[g] == list[g];
+        if (!same) throw std::runtime_error("cannot resume: " + out_path + " holds another galaxy list (use --restart)");
+        for (int g = 0; g < ngal; g++) completed[g] = comp.v[g] > 0.5;
+      }
+    }
+    std::vector<int> todo;
+    for (int g = 0; g < ngal; g++) if (!completed[g]) todo.push_back(g);
+    const size_t n_open = todo.size();
+    if (stop_after >= 0 && todo.size() > (size_t)stop_after) todo.resize((size_t)stop_after);
+    if (dry_run) std::printf("resume %s: %zu of %d galaxies completed, %zu to solve now\n", prev ? "yes" : "no", ngal - n_open, ngal, todo.size());
     if (dry_run) {  // host-side logic only (parameter file, input file, galaxy list, quantity list): no device needed
       std::printf("dry-run ngal %d nz %d list %zu p_courant_v %.17g p_nx_ref %d p_random_seed %d\n", in.ngal, nz, list.size(),
                   cfg.params.p_courant_v, cfg.params.p_nx_ref, cfg.params.p_random_seed);
@@ -271,61 +299,90 @@ int main(int argc, char** argv) {
       if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) throw std::runtime_error("no CUDA device (there is no CPU fallback)");
       for (int d = 0; d < nd; d++) devices.push_back(d);
     }
-    std::vector<double> profiles((size_t)pq.size() * ngal * nz * nr), scalars((size_t)sq.size() * ngal * nz);
-    std::vector<char> status((size_t)ngal * nz);
-    std::vector<int32_t> nsteps(ngal), error(ngal), done(devices.size()), stolen(devices.size());
-    std::vector<int64_t> stages(ngal);
-    std::vector<uint32_t> flags(ngal);
+    const int nsel = (int)todo.size();
+    std::vector<int32_t> sel_ids(nsel);
+    std::vector<double> sel_inputs((size_t)13 * nsel * nz);
+    for (int k = 0; k < nsel; k++) sel_ids[k] = list[todo[k]];
+    for (int c = 0; c < 13; c++)
+      for (int k = 0; k < nsel; k++)
+        std::memcpy(&sel_inputs[((size_t)c * nsel + k) * nz], &inputs[((size_t)c * ngal + todo[k]) * nz], sizeof(double) * nz);
+    std::vector<double> profiles((size_t)pq.size() * nsel * nz * nr), scalars((size_t)sq.size() * nsel * nz);
+    std::vector<char> status((size_t)nsel * nz);
+    std::vector<int32_t> nsteps(nsel), error(nsel), done(devices.size()), stolen(devices.size());
+    std::vector<int64_t> stages(nsel);
+    std::vector<uint32_t> flags(nsel);
     mag_outputs_t out{profiles.data(), scalars.empty() ? nullptr : scalars.data(), status.data(), nsteps.data(), error.data(),
                       stages.data(), flags.data()};
-    std::printf("Magnetizer (B200 path): '%s'  %d galaxies x %d snapshots, %zu GPU(s), chunk %d\n", cfg.model_name.c_str(), ngal, nz,
-                devices.size(), chunk);
+    std::printf("Magnetizer (B200 path): '%s'  %d galaxies x %d snapshots (%zu already completed, %d to solve), %zu GPU(s), chunk %d\n",
+                cfg.model_name.c_str(), ngal, nz, ngal - n_open, nsel, devices.size(), chunk);
     const auto t0 = std::chrono::steady_clock::now();
-    const int rc = mag_solve_partitioned(&cfg.params, (int)devices.size(), devices.data(), ngal, list.data(), nz, in.t_gyr.data(),
-                                         inputs.data(), (int)pq.size(), pq.data(), (int)sq.size(), sq.data(), &out, chunk,
-                                         done.data(), stolen.data());
+    if (nsel > 0) {
+      const int rc = mag_solve_partitioned(&cfg.params, (int)devices.size(), devices.data(), nsel, sel_ids.data(), nz, in.t_gyr.data(),
+                                           sel_inputs.data(), (int)pq.size(), pq.data(), (int)sq.size(), sq.data(), &out, chunk,
+                                           done.data(), stolen.data());
+      if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
+    }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
-    // ---- write_output (output.f90:23-236): unit conversion, [ngal][nx][nz] layout, Log group
-    if (out_path.empty()) out_path = cfg.output_file_name.empty() ? "magnetizer_b200_output.hdf5" : cfg.output_file_name;
-    const bool as_npz = out_path.size() > 4 && out_path.compare(out_path.size() - 4, 4, ".npz") == 0;
+    // ---- write_output (output.f90:23-236): unit conversion, [ngal][nx][nz] layout, Log group.
+    // Galaxies completed by an earlier invocation keep their rows, galaxies not solved yet hold
+    // "never written" markers and completed = 0.
+    const std::string tmp_path = out_path + ".tmp";
     OutputFile w;
     if (as_npz) {
-      w.npz.reset(new NpzWriter(out_path));
-      if (!w.npz->ok()) throw std::runtime_error("cannot write " + out_path);
+      w.npz.reset(new NpzWriter(tmp_path));
+      if (!w.npz->ok()) throw std::runtime_error("cannot write " + tmp_path);
     } else {
-      w.h5.reset(new maghost::Hdf5Writer(out_path));
+      w.h5.reset(new maghost::Hdf5Writer(tmp_path));
       w.h5->add_group("Output");
       w.h5->add_group("Log");
       write_parameter_attributes(*w.h5, cfg);
     }
-    std::vector<double> tmp((size_t)ngal * nr * nz);
+    auto previous = [&](const std::string& path, size_t n) {   // dataset of the resumed file or "never written"
+      if (!prev) return std::vector<double>(n, MAG_INVALID);
+      maghost::H5Reader::Data d = prev->read(path);
+      if (d.v.size() != n) throw std::runtime_error("cannot resume: " + path + " has another shape (use --restart)");
+      return d.v;
+    };
     long long total_stages = 0;
     for (auto s : stages) total_stages += s;
     for (size_t q = 0; q < pq.size(); q++) {
       const std::string name = kProfileNames[pq[q]];
       const double fac = unit_factor(name);
-      const double* src = &profiles[q * (size_t)ngal * nz * nr];
-      for (int g = 0; g < ngal; g++)
+      const double* src = &profiles[q * (size_t)nsel * nz * nr];
+      std::vector<double> full = previous("Output/" + std::string(name == "rkpc" && !have_rkpc ? "r" : name), (size_t)ngal * nr * nz);
+      for (int k = 0; k < nsel; k++)
         for (int iz = 0; iz < nz; iz++)
           for (int i = 0; i < nr; i++) {
-            const double v = src[((size_t)g * nz + iz) * nr + i];
-            tmp[((size_t)g * nr + i) * nz + iz] = (v == MAG_INVALID) ? v : v * fac;
+            const double v = src[((size_t)k * nz + iz) * nr + i];
+            full[((size_t)todo[k] * nr + i) * nz + iz] = (v == MAG_INVALID) ? v : v * fac;
           }
-      if (name != "rkpc" || have_rkpc) w.add_f64("Output", name, {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data());
-      if (name == "rkpc") w.add_f64("Output", "r", {(size_t)ngal, (size_t)nr, (size_t)nz}, tmp.data());
+      if (name != "rkpc" || have_rkpc) w.add_f64("Output", name, {(size_t)ngal, (size_t)nr, (size_t)nz}, full.data());
+      if (name == "rkpc") w.add_f64("Output", "r", {(size_t)ngal, (size_t)nr, (size_t)nz}, full.data());
     }
-    for (size_t q = 0; q < sq.size(); q++)
-      w.add_f64("Output", kScalarNames[sq[q]], {(size_t)ngal, (size_t)nz}, &scalars[q * (size_t)ngal * nz]);
-    w.add_status({(size_t)ngal, (size_t)nz}, status.data());
-    std::vector<double> log_n(ngal), log_c(ngal), log_rt(ngal);
+    for (size_t q = 0; q < sq.size(); q++) {
+      std::vector<double> full = previous(std::string("Output/") + kScalarNames[sq[q]], (size_t)ngal * nz);
+      for (int k = 0; k < nsel; k++)
+        std::memcpy(&full[(size_t)todo[k] * nz], &scalars[(q * (size_t)nsel + k) * nz], sizeof(double) * nz);
+      w.add_f64("Output", kScalarNames[sq[q]], {(size_t)ngal, (size_t)nz}, full.data());
+    }
+    std::vector<char> status_full((size_t)ngal * nz, '-');
+    if (prev) {
+      const std::vector<double> st = previous("Log/status", (size_t)ngal * nz);
+      for (size_t i = 0; i < st.size(); i++) status_full[i] = (char)(int)st[i];
+    }
+    for (int k = 0; k < nsel; k++) std::memcpy(&status_full[(size_t)todo[k] * nz], &status[(size_t)k * nz], nz);
+    w.add_status({(size_t)ngal, (size_t)nz}, status_full.data());
+    std::vector<double> log_n = prev ? previous("Log/nsteps", ngal) : std::vector<double>(ngal, 0.0);
+    std::vector<double> log_c = prev ? previous("Log/completed", ngal) : std::vector<double>(ngal, 0.0);
+    std::vector<double> log_rt = prev ? previous("Log/runtime", ngal) : std::vector<double>(ngal, 0.0);
     std::map<char, long> counts;
-    for (int g = 0; g < ngal; g++) {
-      log_n[g] = nsteps[g];
-      log_c[g] = error[g] ? 0.0 : 1.0;  // Log/completed is only written when runtime > 0 (distributor.f90:363)
-      log_rt[g] = total_stages > 0 ? secs * (double)stages[g] / (double)total_stages : 0.0;
-      for (int iz = 0; iz < nz; iz++) counts[status[(size_t)g * nz + iz]]++;
+    for (int k = 0; k < nsel; k++) {
+      const int g = todo[k];
+      log_n[g] = nsteps[k];
+      log_c[g] = error[k] ? 0.0 : 1.0;  // Log/completed is only written when runtime > 0 (distributor.f90:363)
+      log_rt[g] = total_stages > 0 ? secs * (double)stages[k] / (double)total_stages : 0.0;
     }
+    for (char c : status_full) counts[c]++;
     // Log datasets are (ngals, 1) in the reference's file (Fortran (1, ngals), output.f90:37-54)
     const std::vector<size_t> log_shape = as_npz ? std::vector<size_t>{(size_t)ngal} : std::vector<size_t>{(size_t)ngal, 1};
     w.add_f64("Log", "nsteps", log_shape, log_n.data());
@@ -334,7 +391,9 @@ int main(int argc, char** argv) {
     w.add_i32("Log", "gal_id", {(size_t)ngal}, list.data());
     if (as_npz) w.add_f64("Input", "t", {(size_t)nz}, in.t_gyr.data());
     w.close();
-    std::printf("  solved in %.3f s  (%.1f galaxies/s, %.3e point-stages/s)\n", secs, ngal / secs, total_stages / secs);
+    prev.reset();
+    if (std::rename(tmp_path.c_str(), out_path.c_str()) != 0) throw std::runtime_error("cannot rename " + tmp_path + " to " + out_path);
+    std::printf("  solved in %.3f s  (%.1f galaxies/s, %.3e point-stages/s)\n", secs, nsel / secs, total_stages / secs);
     for (size_t d = 0; d < devices.size(); d++)
       std::printf("  GPU %d: %d chunks (%d stolen)\n", devices[d], done[d], stolen[d]);
     std::printf("  status codes:");

@@ -38,6 +38,8 @@ int main(int argc, char** argv) {
       for (int g = 0; g < ngal; g++) { one[g] = g + 0.25; ids[g] = g + 1; }
       w.add_dataset("Log", "runtime", maghost::Hdf5Writer::F64, {(uint64_t)ngal, 1}, one.data(), {{"Units", "s"}});
       w.add_dataset("Log", "gal_id", maghost::Hdf5Writer::I32, {(uint64_t)ngal}, ids.data());
+      for (int g = 0; g < ngal; g++) one[g] = (g % 3 == 0) ? 1.0 : 0.0;
+      w.add_dataset("Log", "completed", maghost::Hdf5Writer::F64, {(uint64_t)ngal, 1}, one.data());
       w.close();
     }
     maghost::H5Reader r(argv[1]);

@@ -46,6 +46,22 @@ def test_single_galaxy_list_and_namelist_overrides(exe, tmp_path):
     assert (int(m[1]), float(m[2]), int(m[3]), int(m[4])) == (2, 0.09, 51, 5)
 
 
+def test_resume_filtering_from_log_completed(exe, tmp_path):
+    """The output file doubles as checkpoint (distributor.f90:150-156): galaxies whose Log/completed flag
+    is set are skipped (IO_hdf5.f90:244-266); --restart ignores the file, --stop-after N is the graceful
+    stop.  Host logic only (--dry-run); the file is written by the HDF5 writer probe."""
+    probe, out = str(tmp_path / "probe"), str(tmp_path / "out.hdf5")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", probe, os.path.join(ROOT, "tests", "hdf5_writer_probe.cpp"), "-lz"])
+    subprocess.check_call([probe, out, "7", "11", "5"], stdout=subprocess.DEVNULL)   # galaxies 1..7, completed: 1, 4, 7
+    ids = [str(i) for i in range(1, 8)]
+    run = lambda *extra: subprocess.run([exe, PARAMS, *ids, "--out", out, "--dry-run", *extra], cwd=ROOT, capture_output=True, text=True)
+    assert "resume yes: 3 of 7 galaxies completed, 4 to solve now" in run().stdout
+    assert "resume yes: 3 of 7 galaxies completed, 2 to solve now" in run("--stop-after", "2").stdout
+    assert "resume no: 0 of 7 galaxies completed, 7 to solve now" in run("--restart").stdout
+    other = subprocess.run([exe, PARAMS, "1", "2", "3", "--out", out, "--dry-run"], cwd=ROOT, capture_output=True, text=True)
+    assert other.returncode == 1 and "cannot resume" in other.stderr and "--restart" in other.stderr
+
+
 def test_no_cpu_fallback(exe):
     import torch
     if torch.cuda.is_available():
@@ -85,6 +101,21 @@ def test_driver_end_to_end_example(exe, oracle, example_input, tmp_path):
     assert f1["Output/Br"].shape == (1, 101, 40) and f1["Log/status"].shape == (1, 40) and f1["Log/nsteps"].shape == (1, 1)
     assert f1["Log/status"].tobytes() == ora["status"][0].tobytes()
     assert f1.attrs("Output/Br")["Units"] == "microgauss" and f1.attrs("Output/h")["Description"] == "Disk scaleheight"
+    # interrupted run + resume == straight run (the output file is the checkpoint)
+    part, full = str(tmp_path / "resumed.hdf5"), str(tmp_path / "straight.hdf5")
+    gl = ["3", "24", "60", "101"]
+    log_a = subprocess.check_output([exe, PARAMS, *gl, "--out", part, "--stop-after", "2"], cwd=ROOT, text=True)
+    fa = H5File(part)
+    assert "(0 already completed, 2 to solve)" in log_a and fa["Log/completed"].ravel().tolist() == [1.0, 1.0, 0.0, 0.0]
+    assert fa["Log/status"][2].tobytes() == b"-" * 40 and np.all(fa["Output/Br"][2:] == -99999.0)
+    log_b = subprocess.check_output([exe, PARAMS, *gl, "--out", part], cwd=ROOT, text=True)
+    assert "(2 already completed, 2 to solve)" in log_b
+    subprocess.check_call([exe, PARAMS, *gl, "--out", full], cwd=ROOT, stdout=subprocess.DEVNULL)
+    fb, fc = H5File(part), H5File(full)
+    assert fb["Log/completed"].ravel().tolist() == [1.0] * 4 and fb.keys("Output") == fc.keys("Output")
+    for k in fc.keys("Output"):
+        assert np.array_equal(fb["Output/" + k], fc["Output/" + k]), k
+    assert fb["Log/status"].tobytes() == fc["Log/status"].tobytes() and np.array_equal(fb["Log/nsteps"], fc["Log/nsteps"])
     root = f1.attrs("/")
     assert "P_NX_REF=101," in root["grid_parameters"] and root["run_parameters"].startswith("&RUN_PARAMETERS ")
     assert float(re.search(r"P_COURANT_V=([^,]+),", root["run_parameters"])[1]) == 0.09000000357627869
