@@ -11,7 +11,7 @@
 // known for every snapshot, the exact cost of every galaxy is known before Phase B starts
 // and the B queue is ordered longest-first.
 //
-// Phase B (run_evolve, one 2-warp team per galaxy) owns the field f = (Br, Bp, alp_m):
+// Phase B (run_evolve, one warp per galaxy; one 4-warp team in the MAG_TEAM = 128 build) owns the field f = (Br, Bp, alp_m):
 // seeds (seed_field.f90), the field part of adjust_grid, the RK3 time loop with retries
 // (dynamo.f90:155-243), the floor-field RNG stream, and the output rows that depend on f.
 // The "profile refresh stays inside the same solve": both phases run inside one

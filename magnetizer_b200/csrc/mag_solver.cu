@@ -90,13 +90,16 @@ __global__ void __launch_bounds__(128) k_chains(KernelArgs a) {
 }
 
 // ------------------------------------------------------------------ Phase B kernel
-// One 64-thread team per galaxy, persistent, longest history first.  Warp 0 leads (seeds,
-// grid transformations of f, outputs, generic path); warp 1 joins for the fast time loop.
+// One team of MAG_TEAM threads per galaxy, persistent, longest history first.  MAG_TEAM = 32
+// (default build): the team is ONE warp that does everything, the time loop in registers with
+// shuffles (mag_rk_warp.cuh).  MAG_TEAM = 128 (grids of more than 256 points): warp 0 leads
+// (seeds, grid transformations of f, outputs, generic path), the helper warps join for the
+// shared-line time loop (mag_rk_fast.cuh).
 __global__ void __maxnreg__(MAG_EVOLVE_MAXREG) k_evolve(KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RkShared* rs = reinterpret_cast<RkShared*>(smem_raw);
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x >= 32) {  // helper warp
+  if (threadIdx.x >= 32) {  // helper warps (MAG_TEAM > 32 only)
     for (;;) {
       __syncthreads();
       if (rs->call.cmd == TEAM_CMD_EXIT) break;
