@@ -294,6 +294,10 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
     for (int j = 0; j < PPL; j++) { B2[j] = S.f[1][j] * S.f[1][j]; bb[j] = S.f[0][j] * S.f[1][j]; }
 #pragma unroll
     for (int j = 0; j < PPL; j++) { h[j] = fma(-g[j], h[j], 0.5); B2[j] = fma(S.f[0][j], S.f[0][j], B2[j]); }
+#ifdef MAG_TRACK_B2   // staged for the next round: |B| bound from Br^2 + Bp^2 (>= +0: unsigned order of the high words)
+#pragma unroll
+    for (int j = 0; j < PPL; j++) mBu = max(mBu, (unsigned)__double2hiint(B2[j]));
+#endif
 #pragma unroll
     for (int j = 0; j < PPL; j++) { g[j] = fma(g[j], h[j], g[j]); B2[j] = al[j] * B2[j]; }
 #pragma unroll
@@ -361,8 +365,10 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
       else S.ft[v][j] = fma(dz, v == 0 ? p0[j] : (v == 1 ? p1[j] : p2[j]), S.f[v][j]);
     }
     // |x| maxima on the high words: signed max catches the positive values, unsigned max the negative ones
+#ifndef MAG_TRACK_B2
     mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(S.f[0][j]), __double2hiint(S.f[1][j]));
     mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(S.f[0][j]), (unsigned)__double2hiint(S.f[1][j]));
+#endif
     mAs = (unsigned)max((int)mAs, __double2hiint(S.f[2][j]));
     mAu = max(mAu, (unsigned)__double2hiint(S.f[2][j]));
   }
@@ -508,8 +514,10 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
     unsigned mBs = 0, mBu = 0, mAs = 0, mAu = 0;   // running maxima start from the block's initial state
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
+#ifndef MAG_TRACK_B2   // (with MAG_TRACK_B2 the first stage of the block sees this state as its input)
       mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(S.f[0][j]), __double2hiint(S.f[1][j]));
       mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(S.f[0][j]), (unsigned)__double2hiint(S.f[1][j]));
+#endif
       mAs = (unsigned)max((int)mAs, __double2hiint(S.f[2][j]));
       mAu = max(mAu, (unsigned)__double2hiint(S.f[2][j]));
     }
@@ -561,7 +569,17 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
     }
     // ---- accept or replay the block.  Per-lane maxima of lanes 0,1 / tm-1,tm bound the 7 points
     // next to the inner / outer boundary (a superset of them: conservative).
+#ifdef MAG_TRACK_B2
+    // the stages tracked Br^2 + Bp^2 of their INPUT states; add the final state of the block, then
+    // turn the bound on B^2 into one on |B| (one ulp of slack on the high word each way)
+#pragma unroll
+    for (int j = 0; j < PPL; j++) mBu = max(mBu, (unsigned)__double2hiint(fma(S.f[0][j], S.f[0][j], S.f[1][j] * S.f[1][j])));
+    const unsigned mB = mBu >= 0x7fe00000u ? mBu : (unsigned)__double2hiint(sqrt(__hiloint2double((int)mBu + 1, 0)));
+    const unsigned mA = max(mAs, mAu & 0x7fffffffu);
+    (void)mBs;
+#else
     const unsigned mB = max(mBs, mBu & 0x7fffffffu), mA = max(mAs, mAu & 0x7fffffffu);
+#endif
     const unsigned nB0 = max(__shfl_sync(FULL, mB, 0), __shfl_sync(FULL, mB, 1));
     const unsigned nA0 = max(__shfl_sync(FULL, mA, 0), __shfl_sync(FULL, mA, 1));
     const unsigned nB1 = max(__shfl_sync(FULL, mB, tm), __shfl_sync(FULL, mB, tm - 1));
