@@ -77,6 +77,9 @@ struct RkShared {
   // 16-byte aligned vector loads); for COEF_WSMEM the stencil weights [k][slot*64 + thread]
   // follow the short lines
   alignas(16) double pool[(2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM) > 1920 ? (2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM) : 1920];
+#ifdef MAG_WARP_SMEM_EXCHANGE
+  alignas(16) double xch[2][3][32 * 6];   // staged experiment (mag_rk_warp.cuh): halo exchange lines, 48-byte lane stride
+#endif
 };
 static_assert(2 * 3 * MAG_LINE_L <= 2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM, "RkShared pool too small for the long lines");
 

@@ -66,6 +66,11 @@ __device__ __forceinline__ double2 lds_pair(unsigned saddr) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(saddr));
   return r;
 }
+__device__ __forceinline__ double lds_f64x(unsigned saddr) {
+  double r;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(saddr));
+  return r;
+}
 __device__ __forceinline__ double2 ldg_pair(const double2* p) {
   double2 r;
   asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
@@ -80,6 +85,9 @@ template <int PPL, int MODE>
 struct WarpState {
   double f[3][PPL], ft[3][PPL];
   double hl[3][3], hr[3][3];   // halo: the last 3 registers of lane-1, the first 3 of lane+1 (filled by warp_exchange)
+#ifdef MAG_WARP_SMEM_EXCHANGE
+  unsigned xaddr; int xbuf;    // shared address of RkShared::xch, current buffer
+#endif
   double w[MODE == WM_REGS ? PPL : 1][8];
   double ca[MODE == WM_ALLG ? 1 : PPL], gs[MODE == WM_ALLG ? 1 : PPL], c0[MODE == WM_ALLG ? 1 : PPL];
   double fk[MODE == WM_ALLG ? 1 : PPL], ak[MODE == WM_ALLG ? 1 : PPL];
@@ -353,14 +361,51 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
   for (int j = 0; j < PPL; j++) {
     S.f[0][j] = fma(dg, p0[j], S.ft[0][j]); S.f[1][j] = fma(dg, p1[j], S.ft[1][j]); S.f[2][j] = fma(dg, p2[j], S.ft[2][j]);
   }
+#ifdef MAG_WARP_SMEM_EXCHANGE
+  // Staged experiment for the next round (not validated on the GPU): exchange through two
+  // shared-memory lines instead of 36 shuffles -- (PPL+1)/2 stores and 4 loads per variable, a
+  // 48-byte lane stride keeps the 128-bit accesses conflict free, one __syncwarp per stage
+  // (the buffers alternate, so a lane that runs ahead never overwrites what another still reads).
+  constexpr bool kSmemX = PPL <= 6;
+  if (kSmemX) {
+    const unsigned base = S.xaddr + (unsigned)S.xbuf * (3u * 32u * 48u);
+    S.xbuf ^= 1;
+    const int lane_ = (int)(threadIdx.x & 31);
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+      const unsigned row = base + (unsigned)v * (32u * 48u) + (unsigned)lane_ * 48u;
+#pragma unroll
+      for (int j = 0; j + 1 < PPL; j += 2)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row + 8u * j), "d"(S.f[v][j]), "d"(S.f[v][j + 1]) : "memory");
+      if (PPL % 2) asm volatile("st.shared.f64 [%0], %1;" ::"r"(row + 8u * (PPL - 1)), "d"(S.f[v][PPL - 1]) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+      const unsigned lrow = base + (unsigned)v * (32u * 48u) + (unsigned)max(lane_ - 1, 0) * 48u + 8u * (PPL - 3);
+      const unsigned rrow = base + (unsigned)v * (32u * 48u) + (unsigned)min(lane_ + 1, 31) * 48u;
+      if ((PPL - 3) % 2) {   // first of the three is 8-byte aligned only
+        S.hl[v][0] = lds_f64x(lrow);
+        const double2 t = lds_pair(lrow + 8u); S.hl[v][1] = t.x; S.hl[v][2] = t.y;
+      } else {
+        const double2 t = lds_pair(lrow); S.hl[v][0] = t.x; S.hl[v][1] = t.y;
+        S.hl[v][2] = lds_f64x(lrow + 16u);
+      }
+      const double2 t = lds_pair(rrow); S.hr[v][0] = t.x; S.hr[v][1] = t.y;
+      S.hr[v][2] = lds_f64x(rrow + 16u);
+    }
+  }
+#else
+  constexpr bool kSmemX = false;
+#endif
   // the new state is final: the halo exchange for the next stage starts now; its 36 shuffles
   // (one issue slot every ~4 cycles) are interleaved with the ftmp update and the maxima
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
 #pragma unroll
     for (int v = 0; v < 3; v++) {
-      if (j < 3) S.hr[v][j] = shfl_down1(S.f[v][j]);
-      if (j >= PPL - 3) S.hl[v][j - (PPL - 3)] = shfl_up1(S.f[v][j]);
+      if (!kSmemX && j < 3) S.hr[v][j] = shfl_down1(S.f[v][j]);
+      if (!kSmemX && j >= PPL - 3) S.hl[v][j - (PPL - 3)] = shfl_up1(S.f[v][j]);
       if (LAST) S.ft[v][j] = S.f[v][j];
       else S.ft[v][j] = fma(dz, v == 0 ? p0[j] : (v == 1 ? p1[j] : p2[j]), S.f[v][j]);
     }
@@ -401,6 +446,11 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
   double2* const wt2 = reinterpret_cast<double2*>(rs->pool) + lane;                          // shared pair table, this lane's column
   double2* const tab = reinterpret_cast<double2*>(W + (size_t)WARP_TABLE_ARRAY * nxcap) + lane;   // global pair table
   const unsigned wsa = (unsigned)__cvta_generic_to_shared(rs->pool) + 16u * lane;
+#ifdef MAG_WARP_SMEM_EXCHANGE
+#define MAG_WARP_SMEM_EXCHANGE_INIT(S) do { (S).xaddr = (unsigned)__cvta_generic_to_shared(rs->xch); (S).xbuf = 0; } while (0)
+#else
+#define MAG_WARP_SMEM_EXCHANGE_INIT(S) do {} while (0)
+#endif
 
   PHASE_BEGIN;
   prepare_fast_coefs(G, nx);
@@ -411,6 +461,7 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
   PHASE_END(5, lane);
 
   WarpState<PPL, MODE> S;
+  MAG_WARP_SMEM_EXCHANGE_INIT(S);
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
     const int g = g0 + j;
