@@ -3,18 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--ngal G] [--impl b200|reference]
 
-A "step" is one pass of the hot path (mag_solve_batch) over one batch of G synthetic
-Galform-shaped galaxy histories PER GPU (weak scaling; galaxies are independent, there is
-no collective on the solve path).  `value` times the pass with inputs resident in HBM
-(mag_solve_batch_device, CUDA events on the launching stream); `e2e` times the
-reference-facing call with pinned HOST buffers (H2D + kernels + D2H inside the region).
-`--impl reference` times the CPU implementation of the same path (the oracle port of the
-reference's Fortran, which cannot be built here: no gfortran/MPI/HDF5/GSL) on all host
-cores on a bounded sample.
+Workload = BASELINE config 3: ONE synthetic catalogue of G = 1e5 Galform-shaped galaxy histories at
+the default grid, solved on N GPUs (strong scaling: the catalogue is fixed, the GPUs share it).  A
+"step" is one pass of the hot path over the whole catalogue through the multi-GPU partition of the
+C ABI (mag_partition_*: static + work-stealing chunks, no collective on the solve path, results
+gathered in place).  Under torchrun the ranks only rendezvous: rank 0 drives all N GPUs through the
+partition -- the product's own multi-GPU form, one host process like the reference's master -- the
+other ranks hold their barrier.
+
+  value   catalogue resident in HBM (every GPU holds the inputs, rows stay on the GPU that solved
+          them): mag_partition_solve_device, timed with CUDA events on every device, max over GPUs
+  e2e     the reference-facing call with HOST buffers: mag_partition_solve, inputs from page-locked
+          host memory, every result row stored into the caller's page-locked host arrays
+  roofline  k_evolve + k_evolve_heavy of a single-context solve on GPU 0 (one stream, CUDA events)
+  --impl reference  the CPU implementation of the same path (the oracle port of the reference's
+          Fortran, which cannot be built here: no gfortran/MPI/HDF5/GSL) on all host cores, on a
+          bounded sample of the same catalogue
 """
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -29,14 +38,25 @@ sys.path.insert(0, ROOT)
 
 PROFILES = ("Br", "Bp", "alp_m", "h", "n")   # reduced output_quantities_list
 SCALARS = ("Bmax",)
-FLOP_PER_POINT_STAGE = 120.0                 # algorithmic, hoisted RHS (DESIGN.md)
+FLOP_PER_POINT_STAGE = 120.0                 # algorithmic, hoisted RHS (SURVEY.md 8d, DESIGN.md)
+FP64_INSTR_PER_POINT_STAGE = 43.0            # FP64 instructions the loop issues per point and stage
 METRIC = "galaxy histories/sec (FP64, default ngrid)"
-CPU_SAMPLE = 196
+CPU_SAMPLE = 192                             # galaxies of the CPU legs: every (G // 192)-th of the catalogue
+WORKLOAD = "BASELINE config 3: synthetic Galform-shaped galaxy histories, default ngrid (p_nx_ref=101)"
 
 
 def load_base():
     d = np.load(os.path.join(ROOT, "tests", "golden", "example_input.npz"))
     return d["t_gyr"], d["inputs"]
+
+
+def base_config(G, nz):
+    return {"workload": WORKLOAD, "galaxies_total": int(G), "snapshots": int(nz), "outputs": list(PROFILES) + list(SCALARS)}
+
+
+def cpu_sample_ids(G):
+    n = min(CPU_SAMPLE, G)
+    return (np.arange(n, dtype=np.int64) * (G // n)).astype(np.int64)     # 0-based catalogue indices
 
 
 class ClockSampler:
@@ -84,43 +104,52 @@ class ClockSampler:
 
 
 def run_reference(args):
-    """CPU arm: the oracle port of the reference's Fortran path, all host threads."""
+    """CPU arm: the oracle port of the reference's Fortran path, all host threads, on a bounded sample
+    (every (G // 192)-th galaxy) of the same catalogue the GPU arm solves."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle_lib
     oracle_lib.build()
-    from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
+    from magnetizer_b200.synthetic import synthetic_subset
     t, base = load_base()
-    n = CPU_SAMPLE
-    inputs = synthetic_histories(base, n)
-    ids = galaxy_ids(n)
+    G = args.ngal
+    idx = cpu_sample_ids(G)
+    inputs = synthetic_subset(base, idx)
+    ids = (idx + 1).astype(np.int32)
+    n = len(ids)
     p = oracle_lib.default_params()
     cores = os.cpu_count() or 1
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        oracle_lib.solve_batch(p, ids[:cores], t, inputs[:, :cores], profiles=PROFILES, scalars=SCALARS, nthreads=cores)
+    if args.warmup > 0:
+        oracle_lib.solve_batch(p, ids[:cores], t, np.ascontiguousarray(inputs[:, :cores]), profiles=PROFILES, scalars=SCALARS, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         oracle_lib.solve_batch(p, ids, t, inputs, profiles=PROFILES, scalars=SCALARS, nthreads=cores)
     dt = (time.perf_counter() - t0) / args.steps
     v = n / dt
-    sample = f"first {n} galaxies of the synthetic catalogue (= the 196 example histories), {args.steps} pass(es)"
+    sample = (f"{n} galaxies = every {G // n}-th of the {G}-galaxy catalogue per step (the slice bench.py's GPU arm "
+              f"checks against the oracle), {args.steps} step(s), {cores} threads with a shared work counter")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "galaxies/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic Galform-shaped galaxy histories, default ngrid (p_nx_ref=101)",
-                   "galaxies_per_step": n},
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": base_config(G, t.size),
         "cpu_baseline": {"value": v, "unit": "galaxies/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "galaxies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def ncu_metrics():
+    """ncu-derived numbers of the dominant kernel on the bench mix (committed summary, see profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_k_evolve_ncu.json")))
+    except (OSError, ValueError):
+        return {}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from magnetizer_b200.abi import PROFILE_ID  # noqa: F401
-    from magnetizer_b200.solver import DynamoSolver
+    from magnetizer_b200.solver import DynamoSolver, Partition, host_array, host_free
     from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
 
     rank = int(os.environ.get("RANK", "0"))
@@ -130,150 +159,217 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    gloo = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(hours=2))
+        one = torch.ones(1, device=dev)
+        dist.all_reduce(one)                       # NCCL is up on every rank (it carries nothing else: no collective on the solve path)
+        assert int(one.item()) == world
+        gloo = dist.new_group(backend="gloo", timeout=datetime.timedelta(hours=2))   # host-side barrier: waiting ranks do not spin on their GPU
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=gloo)
 
+    if rank != 0:
+        # the partition is driven from rank 0 (one host process, one thread pair per GPU); the other
+        # ranks keep the rendezvous: around the timed regions and at the end
+        for _ in range(5):
+            barrier()
+        dist.destroy_process_group()
+        return
+
+    ndev = world
+    if torch.cuda.device_count() < ndev:
+        raise SystemExit(f"bench.py: {ndev} GPUs requested, {torch.cuda.device_count()} visible")
+    devs = [torch.device("cuda", d) for d in range(ndev)]
     t, base = load_base()
-    G = args.ngal
-    nz = t.size
-    inputs = synthetic_histories(base, G, first=rank * G)     # this rank's shard of the catalogue
-    ids = galaxy_ids(G, first=rank * G)
-    solver = DynamoSolver(device=local)
-    nr = solver.params.p_nx_ref
+    G, nz = args.ngal, t.size
+    inputs = synthetic_histories(base, G)
+    ids = galaxy_ids(G)
+    part = Partition(list(range(ndev)))
+    nr = part.params.p_nx_ref
+    chunk = args.chunk
 
-    # ---- HBM-resident arm
-    d_in = torch.from_numpy(inputs).to(dev)
-    d_t = torch.from_numpy(t).to(dev)
-    d_ids = torch.from_numpy(ids).to(dev)
-    d_prof = torch.empty((len(PROFILES), G, nz, nr), dtype=torch.float64, device=dev)
-    d_scal = torch.empty((len(SCALARS), G, nz), dtype=torch.float64, device=dev)
-    d_status = torch.empty((G, nz), dtype=torch.uint8, device=dev)
-    d_nsteps = torch.empty(G, dtype=torch.int32, device=dev)
-    d_error = torch.empty(G, dtype=torch.int32, device=dev)
-    d_ps = torch.empty(G, dtype=torch.int64, device=dev)
-    d_flags = torch.empty(G, dtype=torch.int32, device=dev)
-    d_out = dict(profiles=d_prof.data_ptr(), scalars=d_scal.data_ptr(), status=d_status.data_ptr(),
-                 nsteps=d_nsteps.data_ptr(), error=d_error.data_ptr(), point_stages=d_ps.data_ptr(),
-                 flags=d_flags.data_ptr())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # ---- HBM-resident arm: every GPU holds the catalogue's inputs and full-size output arrays
+    res = []
+    for d in devs:
+        with torch.cuda.device(d):
+            r = dict(inp=torch.from_numpy(inputs).to(d), t=torch.from_numpy(t).to(d), ids=torch.from_numpy(ids).to(d),
+                     prof=torch.empty((len(PROFILES), G, nz, nr), dtype=torch.float64, device=d),
+                     scal=torch.empty((len(SCALARS), G, nz), dtype=torch.float64, device=d),
+                     status=torch.empty((G, nz), dtype=torch.uint8, device=d),
+                     nsteps=torch.empty(G, dtype=torch.int32, device=d), error=torch.zeros(G, dtype=torch.int32, device=d),
+                     ps=torch.zeros(G, dtype=torch.int64, device=d), flags=torch.empty(G, dtype=torch.int32, device=d),
+                     flush=torch.empty(256 << 20, dtype=torch.uint8, device=d))   # > 126 MB L2
+            res.append(r)
+    d_outs = [dict(profiles=r["prof"].data_ptr(), scalars=r["scal"].data_ptr(), status=r["status"].data_ptr(),
+                   nsteps=r["nsteps"].data_ptr(), error=r["error"].data_ptr(), point_stages=r["ps"].data_ptr(),
+                   flags=r["flags"].data_ptr()) for r in res]
+    owner = np.zeros(G, np.int32)
+
+    def sync_all():
+        for d in devs:
+            torch.cuda.synchronize(d)
 
     def step_device():
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        solver.run_device(G, nz, d_ids.data_ptr(), d_t.data_ptr(), d_in.data_ptr(), PROFILES, SCALARS, d_out,
-                          stream=stream.cuda_stream)
-        e1.record(stream)
-        return e0, e1
+        evs = []
+        for d, r in zip(devs, res):
+            with torch.cuda.device(d):
+                r["flush"].fill_(1)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                evs.append([e0, None])
+        sync_all()
+        st = part.solve_device(G, nz, [r["ids"].data_ptr() for r in res], [r["t"].data_ptr() for r in res],
+                               [r["inp"].data_ptr() for r in res], PROFILES, SCALARS, d_outs, chunk=chunk, owner=owner)
+        for d, ev in zip(devs, evs):     # the call returns when every worker stream has drained
+            with torch.cuda.device(d):
+                ev[1] = torch.cuda.Event(enable_timing=True)
+                ev[1].record()
+        return evs, st
 
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    sampler = ClockSampler(0)
+    sampler.start()
     wall0 = time.perf_counter()
-    evs = [step_device() for _ in range(args.steps)]
+    runs = [step_device() for _ in range(args.steps)]
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if sampler else None
-    ms_dev = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    tim_dev = solver.last_timing()
-    launches = tim_dev["kernel_launches"]
-    ms_evolve = tim_dev["ms_kernels"] - tim_dev["ms_profile_phase"]   # k_evolve of the last timed step
-    W_rank = int(d_ps.sum().item())
-    n_err = int(d_error.sum().item())
+    clocks = sampler.stop()
+    # device time of a step = max over the GPUs of (end event - start event) on that GPU
+    ms_dev = float(np.mean([max(a.elapsed_time(b) for a, b in evs) for evs, _ in runs]))
+    st_last = runs[-1][1]
+    pstats = part.stats()
+    launches_step = int(pstats["launches"].sum())
+    busy_ms = pstats["busy_ms"].tolist()
+    W_total = 0
+    n_err = 0
+    for d in range(ndev):
+        m = torch.from_numpy(owner == d).to(devs[d])
+        W_total += int(res[d]["ps"][m].sum().item())
+        n_err += int(res[d]["error"][m].sum().item())
 
-    # ---- end-to-end arm: reference-facing call, pinned host buffers
-    h_in = torch.from_numpy(inputs).pin_memory().numpy()
-    out = solver.alloc_outputs(G, nz, PROFILES, SCALARS, pinned=True)
+    # ---- end-to-end arm: the reference-facing call, page-locked host buffers, results in place
+    h_in = host_array(inputs.shape, np.float64)
+    h_in[...] = inputs
+    out = part.alloc_outputs(G, nz, PROFILES, SCALARS, pinned=True)
     e2e_steps = max(1, min(args.steps, 3))
-    solver.run(ids, t, h_in, profiles=PROFILES, scalars=SCALARS, out=out)
+    part.solve(ids, t, h_in, chunk=chunk, profiles=PROFILES, scalars=SCALARS, out=out)
     barrier()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
-        flush.fill_(1)
-        r = solver.run(ids, t, h_in, profiles=PROFILES, scalars=SCALARS, out=out)
+        for d, r in zip(devs, res):
+            with torch.cuda.device(d):
+                r["flush"].fill_(1)
+        sync_all()
+        r_e2e = part.solve(ids, t, h_in, chunk=chunk, profiles=PROFILES, scalars=SCALARS, out=out)
     barrier()
     ms_e2e = (time.perf_counter() - w0) * 1e3 / e2e_steps
-    tim = solver.last_timing()
-    h2d = inputs.nbytes + t.nbytes + ids.nbytes
+    e2e_stats = part.stats()
+    h2d = inputs.nbytes + t.nbytes * int(r_e2e["chunks_done"].sum()) + ids.nbytes
     d2h = sum(out[k].nbytes for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"))
-    assert np.array_equal(r["point_stages"], d_ps.cpu().numpy()), "e2e and HBM-resident arms disagree"
+    assert int(r_e2e["point_stages"].sum()) == W_total, "e2e and HBM-resident arms disagree"
 
-    red = torch.tensor([ms_dev, ms_e2e, wall * 1e3 / args.steps], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(W_rank), float(G)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_dev_max, ms_e2e_max, ms_wall_max = red.tolist()
-    W_all, G_all = tot.tolist()
-
-    if rank == 0:
+    # ---- roofline of the evolve kernels: one context, one stream, CUDA events (GPU 0, its 1/N of the catalogue)
+    Gs = G // ndev
+    solver = DynamoSolver(device=0)
+    with torch.cuda.device(devs[0]):
+        r0 = res[0]
+        sl_out = dict(profiles=r0["prof"].data_ptr(), scalars=r0["scal"].data_ptr(), status=r0["status"].data_ptr(),
+                      nsteps=r0["nsteps"].data_ptr(), error=r0["error"].data_ptr(), point_stages=r0["ps"].data_ptr(),
+                      flags=r0["flags"].data_ptr())
+        # a contiguous slice [0, Gs) of the full arrays is itself a valid catalogue only for the per-galaxy
+        # arrays; the [q][G][..] planes keep stride G, so solve the slice through the range form
+        stream = torch.cuda.current_stream()
+        for _ in range(2):
+            r0["flush"].fill_(1)
+            solver.run_device_range(G, 0, Gs, nz, r0["ids"].data_ptr(), r0["t"].data_ptr(), r0["inp"].data_ptr(), PROFILES,
+                                    SCALARS, sl_out, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+        solver.device_status()
+        tim = solver.last_timing()
+        W_slice = int(r0["ps"][:Gs].sum().item())
+        info = solver.info()
         fp64_peak = solver.measure_fp64_peak(5)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        flops = FLOP_PER_POINT_STAGE * W_rank / (ms_evolve * 1e-3)
-        alg_bytes = h2d + d2h
-        # CPU baseline on rank 0: the oracle port on a bounded sample of the same workload
-        cpu = None
-        if not args.no_cpu_baseline:
-            from oracle import oracle_lib
-            oracle_lib.build()
-            n = min(CPU_SAMPLE, G)
-            cores = os.cpu_count() or 1
-            c0 = time.perf_counter()
-            ora = oracle_lib.solve_batch(oracle_lib.default_params(), ids[:n], t, np.ascontiguousarray(inputs[:, :n]),
-                                         profiles=PROFILES, scalars=SCALARS, nthreads=cores)
-            cdt = time.perf_counter() - c0
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            from parity import compare
-            sub = {k: (v[:, :n] if k in ("profiles", "scalars") else v[:n]) if isinstance(v, np.ndarray) else v
-                   for k, v in r.items()}
-            rep = compare(sub, ora)
-            cpu = {"value": n / cdt, "unit": "galaxies/s", "cores": cores, "kind": "port",
-                   "sample": f"first {n} galaxies of rank 0's batch, one pass, {cdt:.1f} s; GPU result checked against it "
-                             f"(worst row-relative error {max(rep.values()):.1e})"}
-        line = {
-            "metric": METRIC, "value": G_all / (ms_dev_max * 1e-3), "unit": "galaxies/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev_max, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic Galform-shaped galaxy histories, default ngrid (p_nx_ref=101)",
-                       "galaxies_per_gpu": G, "galaxies_total": int(G_all), "snapshots": int(nz),
-                       "outputs": list(PROFILES) + list(SCALARS), "partition": f"static x{world}, no collective",
-                       "l2": "256 MiB flush write between timed steps",
-                       "point_stages_per_galaxy": W_all / G_all, "galaxies_with_error": n_err},
-            "e2e": {"value": G_all / (ms_e2e_max * 1e-3), "unit": "galaxies/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e_max,
-                    "ms_h2d": tim["ms_h2d"], "ms_kernels": tim["ms_kernels"], "ms_profile_phase": tim["ms_profile_phase"],
-                    "ms_d2h": tim["ms_d2h"]},
-            "gpu_launches": int(launches * args.steps),
-            "roofline": {"bound": "fp64", "achieved": flops / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                         "frac": flops / fp64_peak if fp64_peak else None, "traffic": None,
-                         "kernel": "k_evolve", "flop_per_point_stage": FLOP_PER_POINT_STAGE,
-                         "point_stages_per_launch": W_rank, "kernel_ms": ms_evolve,
-                         "share_of_step": ms_evolve / ms_dev, "profile_phase_ms": tim_dev["ms_profile_phase"],
-                         "fast_path_replays": solver.info()["fast_path_replays"],
-                         "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "hbm": {"achieved": alg_bytes / (ms_dev * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / hbm_peak,
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-            "cpu_baseline": cpu,
-            "clocks": clocks,
-            "wall_ms_per_step": ms_wall_max,
-        }
-        print(json.dumps(line))
+    ms_evolve = tim["ms_kernels"] - tim["ms_profile_phase"]
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    flops = FLOP_PER_POINT_STAGE * W_slice / (ms_evolve * 1e-3)
+    alg_bytes = h2d + d2h
+    ncu = ncu_metrics()
+
+    # ---- CPU baseline on the host cores: the oracle port on a bounded sample of the same catalogue,
+    # and the GPU rows of those galaxies checked against it
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle_lib
+        oracle_lib.build()
+        idx = cpu_sample_ids(G)
+        cores = os.cpu_count() or 1
+        sub_in = np.ascontiguousarray(inputs[:, idx])
+        c0 = time.perf_counter()
+        ora = oracle_lib.solve_batch(oracle_lib.default_params(), ids[idx], t, sub_in, profiles=PROFILES, scalars=SCALARS, nthreads=cores)
+        cdt = time.perf_counter() - c0
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from parity import compare
+        sub = {k: (np.asarray(v)[:, idx] if k in ("profiles", "scalars") else np.asarray(v)[idx]) if isinstance(v, np.ndarray) else v
+               for k, v in r_e2e.items() if k not in ("chunks_done", "chunks_stolen")}
+        rep = compare(sub, ora)
+        cpu = {"value": len(idx) / cdt, "unit": "galaxies/s", "cores": cores, "kind": "port",
+               "sample": f"{len(idx)} galaxies = every {G // len(idx)}-th of the catalogue, one pass, {cdt:.1f} s; the e2e arm's rows "
+                         f"of those galaxies checked against it (worst row-relative error {max(rep.values()):.1e})"}
+
+    cfg = base_config(G, nz)
+    cfg.update({"partition": f"mag_partition_solve: {ndev} GPU(s) x 2 host threads, chunks of {pstats['chunk']} galaxies, "
+                             "static share + stealing, no collective",
+                "chunks_done": st_last["chunks_done"].tolist(), "chunks_stolen": st_last["chunks_stolen"].tolist(),
+                "gpu_busy_ms_per_step": [round(x, 1) for x in busy_ms],
+                "l2": "256 MiB flush write on every GPU between timed steps",
+                "point_stages_per_galaxy": W_total / G, "galaxies_with_error": n_err})
+    line = {
+        "metric": METRIC, "value": G / (ms_dev * 1e-3), "unit": "galaxies/s", "n_gpus": ndev,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "e2e": {"value": G / (ms_e2e * 1e-3), "unit": "galaxies/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "steps": e2e_steps,
+                "chunks_done": r_e2e["chunks_done"].tolist(), "chunks_stolen": r_e2e["chunks_stolen"].tolist(),
+                "gpu_busy_ms_per_step": [round(x, 1) for x in e2e_stats["busy_ms"].tolist()]},
+        "gpu_launches": int(launches_step * args.steps),
+        "roofline": {"bound": "fp64", "achieved": flops / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                     "frac": flops / fp64_peak if fp64_peak else None,
+                     "traffic": ncu.get("dram_bytes_per_launch"),
+                     "kernel": "k_evolve (+ k_evolve_heavy, concurrent)", "flop_per_point_stage": FLOP_PER_POINT_STAGE,
+                     "point_stages_per_launch": W_slice, "galaxies_per_launch": Gs, "kernel_ms": ms_evolve,
+                     "share_of_step": ms_evolve / tim["ms_kernels"], "profile_phase_ms": tim["ms_profile_phase"],
+                     "heavy_galaxies": info["heavy_galaxies"], "fast_path_replays": info["fast_path_replays"],
+                     # share of the FP64 pipe's issue slots that carry one of the 43 instructions of a LIVE point
+                     "useful_slot_frac": (FP64_INSTR_PER_POINT_STAGE * W_slice / (ms_evolve * 1e-3)) / (fp64_peak / 2.0)
+                     if fp64_peak else None,
+                     "fp64_pipe_util": ncu.get("fp64_pipe_util"), "ncu_source": ncu.get("source"),
+                     "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                     "hbm": {"achieved": alg_bytes / (ms_e2e * 1e-3) / 1e9, "peak": hbm_peak * ndev, "unit": "GB/s",
+                             "frac": alg_bytes / (ms_e2e * 1e-3) / 1e9 / (hbm_peak * ndev),
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "wall_ms_per_step": wall * 1e3 / args.steps,
+    }
+    print(json.dumps(line))
     solver.close()
+    part.close()
+    host_free(h_in)
+    for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"):
+        host_free(out[k])
+    barrier()
     if world > 1:
         dist.destroy_process_group()
 
@@ -283,10 +379,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--ngal", type=int, default=int(os.environ.get("MAG_BENCH_NGAL", "40000")),
-                    help="galaxies per GPU per step (weak scaling).  The workload is BASELINE config 3's synthetic "
-                         "catalogue; the default batch is large enough that the longest history (800 000 RK steps, "
-                         "~1.8 s on its warp) does not set the step time")
+    ap.add_argument("--ngal", type=int, default=int(os.environ.get("MAG_BENCH_NGAL", "100000")),
+                    help="galaxies of the catalogue (total, shared by the GPUs): BASELINE config 3 = 1e5")
+    ap.add_argument("--chunk", type=int, default=0, help="galaxies per partition chunk (0: four chunks per GPU)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

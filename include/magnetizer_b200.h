@@ -25,13 +25,14 @@
 #ifndef MAGNETIZER_B200_H
 #define MAGNETIZER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define MAG_ABI_VERSION 1
+#define MAG_ABI_VERSION 2
 
 /* Number of per-galaxy input time series, in the order read by
  * load_input_parameters (source/input_parameters.f90:158-170). */
@@ -146,9 +147,28 @@ typedef struct mag_params {
   int32_t p_limit_turbulent_scale;/* 1 */
   int32_t p_allow_positive_shears;/* 0 */
   int32_t seed_choice;            /* 0 = 'random' (only one implemented) */
-  int32_t outflow_type;           /* 0 = 'no_outflow' (only one implemented) */
+  /* outflow_parameters (:303-330), source/outflow.f90:24-121 -- all five prescriptions are
+   * implemented: Uz enters the hoisted coefficients of the RHS (vertical advection of Br, Bp,
+   * alp_m; floor-field source; critical dynamo number) and the 'Uz' output row */
+  int32_t outflow_type;           /* MAG_OUTFLOW_*: 0 = 'no_outflow' */
   int32_t reserved[6];
+  double p_outflow_Lsn;           /* 1d38 */
+  double p_outflow_fOB;           /* 0.7f */
+  double p_outflow_etaSN;         /* 9.4d-3 */
+  double p_tOB;                   /* 3 */
+  double p_N_SN1OB;               /* 40 */
+  double p_outflow_hot_gas_density; /* 1.7d-27 */
+  double p_outflow_nu0;           /* 0.5 */
+  double p_outflow_alphahot;      /* -3.2f */
+  double p_outflow_Vhot;          /* 425 */
 } mag_params_t;
+
+/* p_outflow_type (source/global_input_parameters.f90:306, source/outflow.f90:63-95) */
+#define MAG_OUTFLOW_NONE 0
+#define MAG_OUTFLOW_VTURB 1
+#define MAG_OUTFLOW_WIND 2
+#define MAG_OUTFLOW_SUPERBUBBLE_SIMPLE 3
+#define MAG_OUTFLOW_SUPERBUBBLE 4
 
 /* Writes the reference defaults (with float-rounded literals) into *p. */
 void mag_params_default(mag_params_t *p);
@@ -236,15 +256,86 @@ int mag_solve_batch_device(mag_ctx_t *ctx, int32_t ngal, const int32_t *d_gal_id
                            const mag_outputs_t *d_out, void *cuda_stream);
 
 /*
+ * Range forms, for callers that hold the whole catalogue in one set of arrays and solve it
+ * piecewise (the multi-GPU partition below, a driver that streams a catalogue larger than a
+ * GPU's record memory): `gal_ids`, `inputs` and the arrays of `out` are FULL-catalogue arrays
+ * ([..][ngal_total][..], the layouts of mag_solve_batch); only the rows of catalogue galaxies
+ * [g0, g0+n) are read and written, in place -- no packing copy on either side.
+ *
+ * mag_solve_range_async (HOST arrays) enqueues the copies and kernels and returns; mag_wait
+ * blocks until the call is complete, repeats it with a larger record arena when a grid grew
+ * beyond the budget, and returns the call's status.  One call may be pending per context.
+ * mag_solve_batch(...) == mag_solve_range_async(ngal, 0, ngal, ...) + mag_wait.
+ */
+int mag_solve_range_async(mag_ctx_t *ctx, int32_t ngal_total, int32_t g0, int32_t n,
+                          const int32_t *gal_ids, int32_t nz, const double *t_gyr,
+                          const double *inputs, int32_t n_profile_q, const int32_t *profile_q,
+                          int32_t n_scalar_q, const int32_t *scalar_q, const mag_outputs_t *out);
+int mag_wait(mag_ctx_t *ctx);
+
+/* The same with DEVICE arrays (mag_solve_batch_device == range [0, ngal)). */
+int mag_solve_range_device(mag_ctx_t *ctx, int32_t ngal_total, int32_t g0, int32_t n,
+                           const int32_t *d_gal_ids, int32_t nz, const double *d_t_gyr,
+                           const double *d_inputs, int32_t n_profile_q, const int32_t *profile_q,
+                           int32_t n_scalar_q, const int32_t *scalar_q,
+                           const mag_outputs_t *d_out, void *cuda_stream);
+
+/* Device-side status of the last mag_solve_batch_device / mag_solve_range_device call on this
+ * context, to be called after the caller has synchronised its stream: MAG_OK,
+ * MAG_ERR_NX_OVERFLOW (a grid grew beyond p_nx_MAX / the workspace; the reference stops,
+ * grid.f90:222-226) or MAG_ERR_CUDA (record arena exhausted: results incomplete).  The
+ * host-buffer calls report the same conditions through their return value. */
+int mag_last_device_status(mag_ctx_t *ctx);
+
+/* Page-locked host memory that every GPU of the box can store into (cudaHostAlloc, portable +
+ * mapped).  Output arrays allocated here are written by the kernels directly while the solve
+ * runs; any other page-locked memory (cudaHostRegister, torch pin_memory) works as well. */
+void *mag_host_alloc(size_t bytes);
+void mag_host_free(void *p);
+
+/*
  * Multi-GPU form: replaces the MPI master/worker farm of jobs_distribute
  * (source/distributor.f90:253-384) for this operator.  The catalogue is cut into chunks of
- * `chunk` galaxies; GPU number d of `devices[ndev]` owns the chunks k with k % ndev == d
- * (static share) and steals unclaimed chunks from the other GPUs' shares when its own is
- * exhausted; one host thread per GPU drives mag_solve_batch and the results are gathered
- * into `out` (HOST buffers, same layouts as mag_solve_batch) in galaxy order.  There is no
- * collective: galaxies are independent.  chunks_done / chunks_stolen ([ndev], may be NULL)
- * report how the work ended up distributed.  The same device may be listed more than once.
+ * `chunk` galaxies (chunk <= 0: four chunks per device); GPU number d of `devices[ndev]` owns the chunks k with k % ndev == d
+ * (static share) and steals unclaimed chunks from the tails of the other GPUs' shares when its
+ * own is exhausted.  Every GPU is driven by TWO host threads with one solver context each, so
+ * that the profile phase and the head of one chunk fill the SMs that the tail of the previous
+ * chunk leaves idle; inside a chunk the galaxies are scheduled longest-first with the exact
+ * cost known after the profile phase, the longest ones on four-warp teams.  Inputs are read
+ * from and results stored into the caller's full-catalogue HOST arrays in place (layouts of
+ * mag_solve_batch): that IS the host-side gather, in galaxy order.  Page-locked output arrays
+ * (mag_host_alloc) are stored by the kernels directly; pageable ones are staged in HBM.  There
+ * is no collective: galaxies are independent.
+ *
+ * mag_partition_create builds the contexts and worker threads once; mag_partition_solve runs
+ * one catalogue; stats (may be NULL) receives per device chunks_done[ndev], chunks_stolen[ndev].
+ * mag_solve_partitioned = create + solve + destroy.  The same device may be listed more than once.
  */
+typedef struct mag_partition mag_partition_t;
+int mag_partition_create(const mag_params_t *params, int32_t ndev, const int32_t *devices,
+                         mag_partition_t **part_out);
+void mag_partition_destroy(mag_partition_t *part);
+int mag_partition_solve(mag_partition_t *part, int32_t ngal, const int32_t *gal_ids, int32_t nz,
+                        const double *t_gyr, const double *inputs,
+                        int32_t n_profile_q, const int32_t *profile_q,
+                        int32_t n_scalar_q, const int32_t *scalar_q, const mag_outputs_t *out,
+                        int32_t chunk, int32_t *chunks_done, int32_t *chunks_stolen);
+/*
+ * The same partition with the catalogue RESIDENT IN HBM: d_gal_ids[d], d_t_gyr[d], d_inputs[d]
+ * are device d's own full copies of the inputs, d_out[d] its own full-size output arrays; the
+ * rows of a galaxy end up on the device that solved it, owner[g] (HOST, [ngal], may be NULL)
+ * says which (index into devices).
+ */
+int mag_partition_solve_device(mag_partition_t *part, int32_t ngal, const int32_t *const *d_gal_ids,
+                               int32_t nz, const double *const *d_t_gyr, const double *const *d_inputs,
+                               int32_t n_profile_q, const int32_t *profile_q,
+                               int32_t n_scalar_q, const int32_t *scalar_q, const mag_outputs_t *d_out,
+                               int32_t chunk, int32_t *chunks_done, int32_t *chunks_stolen, int32_t *owner);
+/* Of the last solve on this partition: the chunk size used (chunk <= 0 in a solve call selects it
+ * automatically: four chunks per device), kernel launches per device and the device time
+ * (ms, CUDA events) spent inside the kernels of each device's chunks -- where two chunks of a
+ * device overlap, both count. */
+int mag_partition_stats(mag_partition_t *part, int32_t *chunk_used, int64_t *launches, double *busy_ms);
 int mag_solve_partitioned(const mag_params_t *params, int32_t ndev, const int32_t *devices,
                           int32_t ngal, const int32_t *gal_ids, int32_t nz, const double *t_gyr,
                           const double *inputs, int32_t n_profile_q, const int32_t *profile_q,
@@ -252,11 +343,10 @@ int mag_solve_partitioned(const mag_params_t *params, int32_t ndev, const int32_
                           int32_t chunk, int32_t *chunks_done, int32_t *chunks_stolen);
 const char *mag_partition_last_error(void);
 
-/* Per-phase device time (ms, CUDA events on the solve stream) of the last
- * mag_solve_batch/_device call on this context, after the stream is synchronised:
- * [0] grid + profile kernels, [1] evolve kernel, [2] H2D, [3] D2H.  Returns the
- * number of kernel launches of that call.  [0] = profile phase (k_profiles + queue sort),
- * [1] = all kernels (profile phase + k_evolve). */
+/* Per-phase device time (ms, CUDA events on the solve stream) of the last solve call on this
+ * context, after the stream is synchronised: [0] profile phase (k_profiles, k_chains, queue
+ * sort; first chunk), [1] all kernels (profile phase + evolve kernels), [2] H2D, [3] D2H.
+ * Returns the number of kernel launches of that call. */
 int mag_last_timing(mag_ctx_t *ctx, double ms_out[4]);
 
 /* FP64 DFMA micro-benchmark on the context's device: returns achieved FLOP/s

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-MAG_ABI_VERSION = 1
+MAG_ABI_VERSION = 2
 MAG_NINPUT = 13
 MAG_INVALID = -99999.0
 
@@ -28,6 +28,9 @@ ERROR_NAMES = {0: "MAG_OK", -1: "MAG_ERR_NO_DEVICE", -2: "MAG_ERR_BAD_ARGUMENT",
 
 MAG_RNG_XOSHIRO256SS = 0
 MAG_RNG_XORSHIFT1024S = 1
+
+# p_outflow_type (outflow.f90:63-95)
+OUTFLOW_TYPES = ("no_outflow", "vturb", "wind", "superbubble_simple", "superbubble")
 
 MAG_FLAG_UNINIT_R0 = 1
 MAG_FLAG_SECANT = 2
@@ -88,6 +91,15 @@ class MagParams(C.Structure):
         ("seed_choice", C.c_int32),
         ("outflow_type", C.c_int32),
         ("reserved", C.c_int32 * 6),
+        ("p_outflow_Lsn", C.c_double),
+        ("p_outflow_fOB", C.c_double),
+        ("p_outflow_etaSN", C.c_double),
+        ("p_tOB", C.c_double),
+        ("p_N_SN1OB", C.c_double),
+        ("p_outflow_hot_gas_density", C.c_double),
+        ("p_outflow_nu0", C.c_double),
+        ("p_outflow_alphahot", C.c_double),
+        ("p_outflow_Vhot", C.c_double),
     ]
 
     def as_dict(self):

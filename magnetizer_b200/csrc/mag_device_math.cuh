@@ -28,6 +28,8 @@ namespace magdev {
 #define MAG_KPC_SI (3.08567758135e16 * 1e3)
 #define MAG_HMASS 1.67372e-24
 #define MAG_DISK_SCALE_TO_HALFMASS (1.0 / 1.678346990)
+#define MAG_C_U 0.25   // constants.f90:88, :90
+#define MAG_C_A 1.0
 #define MAG_R_IN 1.0e-7
 #define MAG_NGHOST 3
 

@@ -38,7 +38,7 @@ struct ChainJob;
 enum WsArray {
   A_X = 0, A_RKPC, A_H, A_N, A_L, A_LKPC, A_ETAT, A_TAU, A_BEQ, A_ALPK, A_OM, A_G, A_OMD, A_OMB, A_OMH, A_GB, A_GH,
   A_F0, A_F1, A_F2, A_FT0, A_FT1, A_FT2, A_P0, A_P1, A_P2, A_FB0, A_FB1, A_FB2, A_BZ, A_ALP, A_SIGN,
-  A_OMK, A_GK, A_SIGD, A_SIGS, A_RM, A_RHO, A_HKPC, A_T0, A_T1, A_T2,
+  A_OMK, A_GK, A_SIGD, A_SIGS, A_RM, A_RHO, A_HKPC, A_T0, A_T1, A_T2, A_UZ,
   // hoisted RHS coefficients (per snapshot)
   C_IR, C_C1, C_CA, C_CR, C_KDC, C_FB, C_P3, C_QC, C_W,
   // folded coefficients of the register fast path (mag_rk_fast.cuh), zero at ghost points
@@ -49,22 +49,38 @@ enum WsArray {
 struct KernelArgs {
   mag_params_t P;
   Units U;
-  int32_t ngal, nz;
-  const int32_t* gal_ids;
+  int32_t nz;
   const double* t_gyr;
-  const double* inputs;  // [13][ngal][nz]
-  const int32_t* order;  // [ngal] processing order (cost sorted) or nullptr
+  // Every per-galaxy array below is addressed with the CATALOGUE index of the galaxy through a
+  // VIRTUAL base pointer: the address the array would start at if its first row belonged to
+  // catalogue galaxy 0.  The host subtracts (first galaxy held) * (row size) from the real
+  // pointer, so that one kernel serves whole arrays, chunk-local staging buffers and the
+  // caller's pinned arrays alike (mag_solver.cu: bind_*).  A null pointer skips that output.
+  const int32_t* gal_ids;            // [g]
+  const double* in[MAG_NINPUT];      // per input column: [g][nz]
+  double* prof[MAG_NPROFILE];        // per REQUESTED profile quantity qq: [g][nz][p_nx_ref]
+  double* scal[MAG_NSCALAR];         // per requested scalar quantity: [g][nz]
+  char* o_status;                    // [g][nz]
+  int32_t* o_nsteps;                 // [g]
+  int32_t* o_error;
+  uint32_t* o_flags;
+  int64_t* o_point_stages;
+  const int32_t* order;  // [chunk] processing order of the evolve phase: heavy class first, each class cost sorted
   int32_t n_profile_q, n_scalar_q;
   int32_t profile_q[MAG_NPROFILE];
   int32_t scalar_q[MAG_NSCALAR];
-  mag_outputs_t out;
-  int32_t g0, g1;        // galaxy range of this chunk
+  int32_t g0, g1;        // galaxy range of this chunk (catalogue indices)
   double* ws;            // Phase A: [nwarps][A_COUNT][nxcap]
-  double* ws2;           // Phase B: [nteams][A_COUNT][nxcap]
+  double* ws2;           // Phase B, one-warp teams: [nteams][A_COUNT][nxcap]
+  double* ws3;           // Phase B, four-warp teams
   int32_t nxcap;
   int32_t* counter;      // Phase A work queue head
-  int32_t* counter2;     // Phase B work queue head
-  int32_t* fail;         // device-side error flag (nx overflow)
+  int32_t* counter2;     // Phase B work queue head, one-warp teams (light class)
+  int32_t* counter3;     // Phase B work queue head, four-warp teams (heavy class)
+  const int32_t* n_heavy;  // galaxies of the heavy class = the first *n_heavy entries of `order`
+  unsigned long long* cost_total;  // sum of GalHead::cost over the chunk (profile phase)
+  int32_t* n_invalidated;  // galaxies whose evolve phase rewrote rows of the profile phase (status 'i')
+  int32_t* fail;         // device-side error flag (nx overflow, arena exhausted)
   int32_t use_fast;      // 1: use the register/smem fast path where it applies
   int32_t* replays;      // diagnostic: fast-path blocks replayed with the generic path
   // snapshot records exchanged between the profile phase and the evolve phase (mag_phases.cuh)
@@ -79,6 +95,7 @@ struct KernelArgs {
   int32_t* jobidx;       // [chunk][nz][2] -> index into jobs or -1
   int32_t job_cap;
   int32_t chain_mode;    // CHAIN_MODE_* of this k_profiles launch
+  int32_t pdl_join;      // k_evolve was launched as the programmatic dependent of k_evolve_heavy
 };
 #define MAG_ERR_ARENA (-6)  // internal: record arena exhausted (the host retries with smaller chunks)
 
@@ -121,7 +138,7 @@ struct Gal {
 // input column c at snapshot (1-based) it
 __device__ __forceinline__ double input_at(const Gal& G, int c, int it) {
   const KernelArgs* a = G.a;
-  return a->inputs[((size_t)c * a->ngal + G.g) * a->nz + (it - 1)];
+  return a->in[c][(size_t)G.g * a->nz + (it - 1)];
 }
 
 // load_input_parameters (input_parameters.f90:136-192): init_it / max_it
@@ -446,6 +463,37 @@ __device__ const double* chain_job_array(const Gal& G, int k);
 __device__ uint32_t chain_job_flags(const Gal& G);
 __device__ int chain_import(Gal& G);                          // < 0: not available
 
+// outflow_speed (outflow.f90:24-121) at one radius: r, h in kpc, rho in g/cm^3, vt in km/s -> km/s.
+// Literals without d0 are single precision in the reference.
+struct OutflowCtx { double r_disk, v_disk, SFR; };
+__device__ inline double outflow_speed(const mag_params_t& P, const OutflowCtx& c, double r, double rho, double hk, double vt, double Rm) {
+  switch (P.outflow_type) {
+    case MAG_OUTFLOW_NONE: return r * 0.0;
+    case MAG_OUTFLOW_VTURB: return vt;
+    case MAG_OUTFLOW_WIND: {
+      const double VDISK_MIN = (double)0.01f;
+      const double fm = Rm / (1.0 + Rm);
+      const double beta = detmath::det_pow(fmax(VDISK_MIN, c.v_disk) / P.p_outflow_Vhot, P.p_outflow_alphahot);
+      double u = 0.5 * P.p_outflow_nu0 * beta * hk * fm;
+      u = u * MAG_KM_KPC / (1.e9 * 365.25 * 24 * 3600);
+      return u;
+    }
+    default: break;
+  }
+  const double rs = c.r_disk * MAG_DISK_SCALE_TO_HALFMASS;
+  const double nn = rho / MAG_HMASS;
+  if (!(nn > 0.0)) return 0.0;
+  const double constant = (double)51.3f * detmath::det_pow(P.p_outflow_Lsn / 1e38, (double)(1.f / 3.f)) * P.p_outflow_fOB / 0.7 *
+                          (P.p_outflow_etaSN / (double)9.4e-3f) * (P.p_tOB / 3.0) * (40.0 / P.p_N_SN1OB);
+  const double q = rs / 3.0;
+  double u = constant * (1.0 / (q * q)) * c.SFR;
+  u = u * detmath::det_pow(nn, (double)(-1.f / 3.f));
+  u = u * detmath::det_pow(hk / (double)0.2f, (double)(4.f / 3.f));
+  u = u * detmath::det_exp(-r / rs);
+  if (P.outflow_type == MAG_OUTFLOW_SUPERBUBBLE) u = (P.p_outflow_hot_gas_density / rho) * u;
+  return u;
+}
+
 // ------------------------------------------------------------------ construct_profiles
 // profiles.f90:33-272 (B absent).  Also prepares what set_timestep needs (min h>0, max
 // etat, min tau) and, when the profiles are usable, the hoisted RHS coefficients.
@@ -457,7 +505,7 @@ __device__ inline bool construct_profiles(Gal& G) {
   double *Om_d = G.A(A_OMD), *Om_b = G.A(A_OMB), *Om_h = G.A(A_OMH), *G_b = G.A(A_GB), *G_h = G.A(A_GH);
   double *Omk = G.A(A_OMK), *Gk = G.A(A_GK), *Om = G.A(A_OM), *Gc = G.A(A_G);
   double *h = G.A(A_H), *nn = G.A(A_N), *l = G.A(A_L), *lk = G.A(A_LKPC), *etat = G.A(A_ETAT), *tau = G.A(A_TAU);
-  double *Beq = G.A(A_BEQ), *alp_k = G.A(A_ALPK);
+  double *Beq = G.A(A_BEQ), *alp_k = G.A(A_ALPK), *Uz = G.A(A_UZ);
   bool result = true;
   const double r_disk_min = G.r_max_kpc * P.rmin_over_rmax;
   G.delta_r_floor = P.p_floor_kappa * P.p_ISM_turbulent_length / G.r_max_kpc;
@@ -538,7 +586,7 @@ __device__ inline bool construct_profiles(Gal& G) {
 
   // negligible-disk trap (profiles.f90:131-140)
   if (G.r_disk < r_disk_min || G.Mgas_disk < P.Mgas_disk_min) {
-    for (int i = lane; i < nx; i += 32) { nn[i] = 0; l[i] = 0; h[i] = 0; etat[i] = 0; alp_k[i] = 0; }
+    for (int i = lane; i < nx; i += 32) { nn[i] = 0; l[i] = 0; h[i] = 0; etat[i] = 0; alp_k[i] = 0; Uz[i] = 0; }
     G.minh = 1e10; G.maxetat = 0.0;
     __syncwarp();
     return true;
@@ -595,7 +643,12 @@ __device__ inline bool construct_profiles(Gal& G) {
 
   const double v = G.v_code;
   double mn_h = 1e10, mx_e = -CUDART_INF, mn_tau = CUDART_INF;
+  const OutflowCtx oc = {G.r_disk, G.v_disk, G.SFR};
+  const double* Rmol = G.A(A_RM);
   for (int i = lane; i < nx; i += 32) {
+    // VERTICAL VELOCITY PROFILE (profiles.f90:225-232)
+    const double Uz_kms = result ? outflow_speed(P, oc, rk[i], rho[i], h_kpc[i], v_kms, Rmol[i]) : 0.0;
+    Uz[i] = Uz_kms / U.h0_km * U.t0_s;
     const double n_cm3 = rho[i] / MAG_HMASS;
     const double ni = n_cm3 / U.n0_cm3;
     nn[i] = ni;
@@ -632,21 +685,26 @@ __device__ inline bool construct_profiles(Gal& G) {
     const double pi2 = MAG_PI / 2, pi2_5 = pi2 * pi2 * pi2 * pi2 * pi2;
     const double pi32 = MAG_PI * sqrt(MAG_PI);
     for (int i = lane; i < nx; i += 32) {
-      const double r = x[i], hi = h[i], et = etat[i], li = l[i], be = Beq[i];
+      const double r = x[i], hi = h[i], et = etat[i], li = l[i], be = Beq[i], uz = Uz[i];
       cIR[i] = 1.0 / r;
-      const double c1 = MAG_PI * MAG_PI / 4 / (hi * hi) * et;
+      // vertical advection by the outflow (gutsdynamo.f90:243,253: -C_U*Uz*B/h; :285: -C_a*alp_m*Uz/h) joins the
+      // vertical-diffusion coefficients; with 'no_outflow' uz = 0 and the terms vanish exactly
+      const double c1 = MAG_PI * MAG_PI / 4 / (hi * hi) * et + MAG_C_U * uz / hi;
       cC1[i] = c1;
       cCA[i] = 2.0 / MAG_PI / hi;
       cCR[i] = et * lam2;
       const double kD = Gc[i] * (hi * hi * hi) / (et * et);
-      cKDC[i] = kD / pi2_5;
+      // compute_floor_source_coefficient (floor_field.f90:83-97): R_U = Uz*h/etat,
+      // Dyn_crit = -(pi/2)^5 (1 + 4 C_U R_U/pi^2)^2, A_floor = (pi/2)^2 etat/h^2 (1 + 4 C_U R_U/pi^2)(1 - Dyn_gen/Dyn_crit)
+      const double tU = 1.0 + 4 * MAG_C_U * (uz * hi / et) / (MAG_PI * MAG_PI);
+      cKDC[i] = kD / (pi2_5 * (tU * tU));
       const double Ncells = fabs(3.0 * r * Dr * hi / (li * li * li) / lam2);
       const double b = detmath::det_exp(-Dr / 2. / fabs(r)) * (P.fmag * be) / sqrt(Ncells) * li / Dr * lam / 3 * P.C_floor;
-      cFB[i] = (pi2 * pi2) * et / (hi * hi) * b;
+      cFB[i] = (pi2 * pi2) * et / (hi * hi) * tU * b;
       const double lkr = 1.0 / lk[i];
       cP3[i] = -2 * (lkr * lkr) * et / (be * be);
       cQC[i] = 3 * et / pi32 / hi * sqrt(fabs(kD));
-      cW[i] = P.R_kappa * et * (-(MAG_PI * MAG_PI)) / (hi * hi);
+      cW[i] = P.R_kappa * et * (-(MAG_PI * MAG_PI)) / (hi * hi) - MAG_C_A * uz / hi;
     }
     __syncwarp();
   }
@@ -922,13 +980,14 @@ __device__ inline const double* profile_source(const Gal& G, int q) {
     case MAG_Q_N: return G.A(A_N);
     case MAG_Q_BEQ: return G.A(A_BEQ);
     case MAG_Q_RKPC: return G.A(A_RKPC);
-    default: return nullptr;  // v (constant), Uz, Ur (zero)
+    case MAG_Q_UZ: return G.A(A_UZ);
+    default: return nullptr;  // v (constant), Ur (zero)
   }
 }
 
 // true for the quantities whose rows the evolve phase writes (they depend on f); all other
 // profiles depend on the ISM profiles only and are written by the profile phase
-__device__ __forceinline__ bool is_field_quantity(int q) {
+__host__ __device__ __forceinline__ bool is_field_quantity(int q) {
   return q == MAG_Q_BR || q == MAG_Q_BP || q == MAG_Q_ALP_M || q == MAG_Q_BZMOD || q == MAG_Q_ALP;
 }
 
@@ -936,17 +995,15 @@ __device__ __forceinline__ bool is_field_quantity(int q) {
 __device__ inline void write_profile_rows(Gal& G, int it) {
   const KernelArgs* a = G.a;
   const int nr = a->P.p_nx_ref, ni = G.nx - 2 * MAG_NGHOST, ng = MAG_NGHOST, lane = G.lane;
-  const int nz = a->nz, ngal = a->ngal, g = G.g;
+  const int nz = a->nz;
   G.w0 = min(G.w0, it); G.w1 = max(G.w1, it);
-  if (a->out.profiles) {
-    for (int qq = 0; qq < a->n_profile_q; qq++) {
-      const int q = a->profile_q[qq];
-      if (is_field_quantity(q)) continue;
-      const double* src = profile_source(G, q);
-      double* dst = a->out.profiles + (((size_t)qq * ngal + g) * nz + (it - 1)) * nr;
-      const double cval = (q == MAG_Q_V) ? G.v_code : 0.0;
-      for (int i = lane; i < nr; i += 32) dst[i] = src ? rescale_at(src + ng, ni, i, nr) : cval;
-    }
+  for (int qq = 0; qq < a->n_profile_q; qq++) {
+    const int q = a->profile_q[qq];
+    if (is_field_quantity(q) || !a->prof[qq]) continue;
+    const double* src = profile_source(G, q);
+    double* dst = a->prof[qq] + ((size_t)G.g * nz + (it - 1)) * nr;
+    const double cval = (q == MAG_Q_V) ? G.v_code : 0.0;
+    for (int i = lane; i < nr; i += 32) dst[i] = src ? rescale_at(src + ng, ni, i, nr) : cval;
   }
   __syncwarp();
 }
@@ -956,21 +1013,20 @@ __device__ inline void write_profile_rows(Gal& G, int it) {
 __device__ inline void write_field_rows(Gal& G, int it) {
   const KernelArgs* a = G.a;
   const int nr = a->P.p_nx_ref, ni = G.nx - 2 * MAG_NGHOST, ng = MAG_NGHOST, lane = G.lane;
-  const int nz = a->nz, ngal = a->ngal, g = G.g;
+  const int nz = a->nz;
+  const size_t g = (size_t)G.g;
   const bool alp_ok = (G.status == 'M' || G.status == 'm');
   G.w0 = min(G.w0, it); G.w1 = max(G.w1, it);
-  if (a->out.status && lane == 0) a->out.status[(size_t)g * nz + it - 1] = G.status;
-  if (a->out.profiles) {
-    for (int qq = 0; qq < a->n_profile_q; qq++) {
-      int q = a->profile_q[qq];
-      if (!is_field_quantity(q)) continue;
-      if (q == MAG_Q_ALP && !alp_ok) q = MAG_Q_H;  // ts_arrays.f90:200-201: stale tmp (= h)
-      const double* src = profile_source(G, q);
-      double* dst = a->out.profiles + (((size_t)qq * ngal + g) * nz + (it - 1)) * nr;
-      for (int i = lane; i < nr; i += 32) dst[i] = rescale_at(src + ng, ni, i, nr);
-    }
+  if (a->o_status && lane == 0) a->o_status[g * nz + it - 1] = G.status;
+  for (int qq = 0; qq < a->n_profile_q; qq++) {
+    int q = a->profile_q[qq];
+    if (!is_field_quantity(q) || !a->prof[qq]) continue;
+    if (q == MAG_Q_ALP && !alp_ok) q = MAG_Q_H;  // ts_arrays.f90:200-201: stale tmp (= h)
+    const double* src = profile_source(G, q);
+    double* dst = a->prof[qq] + (g * nz + (it - 1)) * nr;
+    for (int i = lane; i < nr; i += 32) dst[i] = rescale_at(src + ng, ni, i, nr);
   }
-  if (a->out.scalars && a->n_scalar_q > 0) {
+  if (a->n_scalar_q > 0 && a->scal[0]) {
     const double *f0 = G.A(A_F0) + ng, *f1 = G.A(A_F1) + ng, *bz = G.A(A_BZ) + ng, *rk = G.A(A_RKPC) + ng, *h = G.A(A_H) + ng;
     double bmax = -CUDART_INF; int bidx = 0x7fffffff;
     double s_rh = 0, s_b2rh = 0, s_br = 0, s_r = 0;
@@ -999,7 +1055,7 @@ __device__ inline void write_field_rows(Gal& G, int it) {
           case MAG_S_BEAVG: v = (s_rh > 0) ? sqrt(s_b2rh / s_rh) : MAG_INVALID; break;
           default: break;
         }
-        a->out.scalars[((size_t)qq * ngal + g) * nz + it - 1] = v;
+        a->scal[qq][g * nz + it - 1] = v;
       }
     }
   }
@@ -1009,19 +1065,20 @@ __device__ inline void write_field_rows(Gal& G, int it) {
 // fills a galaxy's outputs with "never written" markers (reset_ts_arrays, ts_arrays.f90:205-210)
 __device__ inline void reset_outputs(const Gal& G) {
   const KernelArgs* a = G.a;
-  const int nr = a->P.p_nx_ref, nz = a->nz, ngal = a->ngal, g = G.g, lane = G.lane;
-  if (a->out.profiles)
-    for (int qq = 0; qq < a->n_profile_q; qq++) {
-      double* dst = a->out.profiles + ((size_t)qq * ngal + g) * nz * nr;
-      for (int i = lane; i < nz * nr; i += 32) dst[i] = MAG_INVALID;
-    }
-  if (a->out.scalars)
-    for (int qq = 0; qq < a->n_scalar_q; qq++)
-      for (int i = lane; i < nz; i += 32) a->out.scalars[((size_t)qq * ngal + g) * nz + i] = MAG_INVALID;
+  const int nr = a->P.p_nx_ref, nz = a->nz, lane = G.lane;
+  const size_t g = (size_t)G.g;
+  for (int qq = 0; qq < a->n_profile_q; qq++) {
+    if (!a->prof[qq]) continue;
+    double* dst = a->prof[qq] + g * nz * nr;
+    for (int i = lane; i < nz * nr; i += 32) dst[i] = MAG_INVALID;
+  }
+  for (int qq = 0; qq < a->n_scalar_q; qq++)
+    if (a->scal[qq])
+      for (int i = lane; i < nz; i += 32) a->scal[qq][g * nz + i] = MAG_INVALID;
   // '-' everywhere: the reference's '0' marking only happens for the first galaxy a rank
   // processes (ts_arrays.f90:99-121), an order dependence that is not reproduced
-  if (a->out.status)
-    for (int i = lane; i < nz; i += 32) a->out.status[(size_t)g * nz + i] = '-';
+  if (a->o_status)
+    for (int i = lane; i < nz; i += 32) a->o_status[g * nz + i] = '-';
 }
 
 
@@ -1032,23 +1089,23 @@ __device__ inline void reset_outputs(const Gal& G) {
 // outputs live in mapped host memory and every store crosses PCIe.
 __device__ inline void fill_unwritten(const Gal& G, bool field_part) {
   const KernelArgs* a = G.a;
-  const int nr = a->P.p_nx_ref, nz = a->nz, ngal = a->ngal, g = G.g, lane = G.lane;
+  const int nr = a->P.p_nx_ref, nz = a->nz, lane = G.lane;
+  const size_t g = (size_t)G.g;
   const int w0 = G.w1 >= G.w0 ? G.w0 : nz + 1, w1 = G.w1 >= G.w0 ? G.w1 : nz;   // nothing written: everything is "before"
   for (int part = 0; part < 2; part++) {
     const int s0 = part == 0 ? 1 : w1 + 1, s1 = part == 0 ? w0 - 1 : nz;   // snapshots s0..s1 (1-based)
     if (s1 < s0) continue;
-    if (a->out.profiles)
-      for (int qq = 0; qq < a->n_profile_q; qq++) {
-        if (is_field_quantity(a->profile_q[qq]) != field_part) continue;
-        double* dst = a->out.profiles + (((size_t)qq * ngal + g) * nz + (s0 - 1)) * nr;
-        for (int i = lane; i < (s1 - s0 + 1) * nr; i += 32) dst[i] = MAG_INVALID;
-      }
+    for (int qq = 0; qq < a->n_profile_q; qq++) {
+      if (is_field_quantity(a->profile_q[qq]) != field_part || !a->prof[qq]) continue;
+      double* dst = a->prof[qq] + (g * nz + (s0 - 1)) * nr;
+      for (int i = lane; i < (s1 - s0 + 1) * nr; i += 32) dst[i] = MAG_INVALID;
+    }
     if (field_part) {
-      if (a->out.scalars)
-        for (int qq = 0; qq < a->n_scalar_q; qq++)
-          for (int i = s0 - 1 + lane; i < s1; i += 32) a->out.scalars[((size_t)qq * ngal + g) * nz + i] = MAG_INVALID;
-      if (a->out.status)
-        for (int i = s0 - 1 + lane; i < s1; i += 32) a->out.status[(size_t)g * nz + i] = '-';
+      for (int qq = 0; qq < a->n_scalar_q; qq++)
+        if (a->scal[qq])
+          for (int i = s0 - 1 + lane; i < s1; i += 32) a->scal[qq][g * nz + i] = MAG_INVALID;
+      if (a->o_status)
+        for (int i = s0 - 1 + lane; i < s1; i += 32) a->o_status[g * nz + i] = '-';
     }
   }
   __syncwarp();

@@ -43,10 +43,12 @@ struct SnapRec {       // dense [ngal][nz]
   long long off_pre;   // arena offset of Beq on the pre-adjust grid [nx_pre] (SR_RESEED only)
   double dt, t_Gyr, lambda, delta_r_floor, tau_min, v_code;
 };
-struct GalHead {       // [ngal]
+struct GalHead {       // [chunk]
   int32_t init_it, max_it, error;
   uint32_t flags;
   long long cost;      // sum over SR_SOLVE snapshots of nsteps*nx
+  int32_t nx_max;      // largest grid of an SR_SOLVE snapshot
+  int32_t pad;
 };
 
 struct ChainJob {      // one hydrostatic chain = one construct_profiles call of one galaxy
@@ -159,7 +161,7 @@ __device__ inline bool write_record(Gal& G, int it, int flags, int nx_pre, int n
     for (int i = G.lane; i < nx; i += 32) dst[i] = src[i];
   }
   if (G.lane == 0) {
-    SnapRec& R = a->recs[(size_t)G.g * a->nz + it - 1];
+    SnapRec& R = a->recs[(size_t)(G.g - a->g0) * a->nz + it - 1];   // record tables are chunk-local
     R.flags = flags | SR_VALID; R.nx = nx; R.nx_pre = nx_pre; R.nx_mid = nx_mid; R.nsteps = G.nsteps;
     R.status = (int)G.status; R.off = off; R.off_pre = off_pre;
     R.dt = G.dt; R.t_Gyr = G.t_Gyr; R.lambda = G.lambda; R.delta_r_floor = G.delta_r_floor;
@@ -183,14 +185,14 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
   G.last_output = false;
   G.t = 0; G.dt = 0; G.nsteps = 20; G.time_between_inputs = 0; G.minh = 1e10; G.maxetat = 0; G.tau_min = 0;
   G.t_last_sign_choice = 0; G.refresh_sign = true; G.sign_nx = -1;
-  H.cost = 0; H.flags = 0; H.error = 0;
+  H.cost = 0; H.flags = 0; H.error = 0; H.nx_max = 0; H.pad = 0;
   G.w0 = G.a->nz + 1; G.w1 = 0;   // no output row written yet (k_profiles fills the rest afterwards)
   load_input_parameters(G);
   H.init_it = G.init_it; H.max_it = G.max_it;
   if (set_input_params(G)) return true;
   construct_grid(G);
   {
-    const int ids[] = {A_F0, A_F1, A_F2, A_ALP, A_BZ, A_BEQ, A_TAU, A_LKPC, A_L, A_N, A_H, A_ETAT, A_ALPK,
+    const int ids[] = {A_F0, A_F1, A_F2, A_ALP, A_BZ, A_BEQ, A_TAU, A_LKPC, A_L, A_N, A_H, A_ETAT, A_ALPK, A_UZ,
                        C_IR, C_C1, C_CA, C_CR, C_KDC, C_FB, C_P3, C_QC, C_W, A_G};
     for (int k = 0; k < (int)(sizeof(ids) / sizeof(int)); k++) {
       double* p = G.A(ids[k]);
@@ -255,6 +257,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
     if (!test_run && !elliptical) {
       fl |= SR_SOLVE;
       H.cost += (long long)G.nsteps * G.nx;
+      H.nx_max = max(H.nx_max, G.nx);
     }
     if (G.last_output) fl |= SR_LAST;
     if (!exporting) {
@@ -270,8 +273,8 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
 }
 
 // ------------------------------------------------------------------ Phase B (leader warp)
-struct RkShared;
-__device__ bool run_timesteps(Gal& G, RkShared* rs);   // mag_rk_fast.cuh
+template <int TEAM> struct RkSharedT;
+template <int TEAM> __device__ bool run_timesteps(Gal& G, RkSharedT<TEAM>* rs);   // mag_rk_fast.cuh
 
 // loads the arrays of a record into the team's workspace
 __device__ inline void load_record(Gal& G, const SnapRec& R) {
@@ -288,17 +291,21 @@ __device__ inline void load_record(Gal& G, const SnapRec& R) {
 // early with status 'i', dynamo.f90:245-257)
 __device__ inline void invalidate_later_rows(Gal& G, int it) {
   const KernelArgs* a = G.a;
-  const int nr = a->P.p_nx_ref, nz = a->nz, ngal = a->ngal, g = G.g;
-  if (!a->out.profiles) return;
+  const int nr = a->P.p_nx_ref, nz = a->nz;
+  if (it >= nz) return;
+  // (the host re-copies the rows of the profile phase when they were staged and copied out
+  // while this kernel was running, mag_solver.cu)
+  if (G.lane == 0 && a->n_invalidated) atomicAdd(a->n_invalidated, 1);
   for (int qq = 0; qq < a->n_profile_q; qq++) {
-    if (is_field_quantity(a->profile_q[qq])) continue;
-    double* dst = a->out.profiles + (((size_t)qq * ngal + g) * nz + it) * nr;
+    if (is_field_quantity(a->profile_q[qq]) || !a->prof[qq]) continue;
+    double* dst = a->prof[qq] + ((size_t)G.g * nz + it) * nr;
     for (int i = G.lane; i < (nz - it) * nr; i += 32) dst[i] = MAG_INVALID;
   }
   __syncwarp();
 }
 
-__device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
+template <int TEAM>
+__device__ static void run_evolve(Gal& G, const GalHead& H, RkSharedT<TEAM>* rs) {
   const KernelArgs* a = G.a;
   const mag_params_t& P = a->P;
   const bool test_run = P.p_no_magnetic_fields_test_run != 0;
@@ -314,7 +321,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
   G.t = 0; G.nsteps = 20;
   G.w0 = a->nz + 1; G.w1 = 0;
   G.init_it = H.init_it; G.max_it = H.max_it;
-  const SnapRec* recs = a->recs + (size_t)G.g * a->nz;
+  const SnapRec* recs = a->recs + (size_t)(G.g - a->g0) * a->nz;
   G.nx = recs[H.init_it - 1].nx;
   for (int v = 0; v < 3; v++) { double* f = G.A(A_F0 + v); for (int i = lane; i < G.nx; i += 32) f[i] = 0.0; }
   { double *alp = G.A(A_ALP), *bz = G.A(A_BZ); for (int i = lane; i < G.nx; i += 32) { alp[i] = 0.0; bz[i] = 0.0; } }
@@ -368,7 +375,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
         __syncwarp();
         break;
       }
-      ok = run_timesteps(G, rs);
+      ok = run_timesteps<TEAM>(G, rs);
       if (ok) break;
       G.status = 'm';
       G.flags |= MAG_FLAG_RETRY;
@@ -396,9 +403,9 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkShared* rs) {
   }
   fill_unwritten(G, true);
   if (lane == 0) {
-    if (a->out.nsteps) a->out.nsteps[G.g] = G.nsteps;
-    if (a->out.point_stages) a->out.point_stages[G.g] = G.point_stages;
-    if (a->out.flags) a->out.flags[G.g] = G.flags;
+    if (a->o_nsteps) a->o_nsteps[G.g] = G.nsteps;
+    if (a->o_point_stages) a->o_point_stages[G.g] = G.point_stages;
+    if (a->o_flags) a->o_flags[G.g] = G.flags;
   }
   __syncwarp();
 }

@@ -34,18 +34,21 @@
 namespace magdev {
 
 #define MAG_FAST_BLK 16       // steps per checkpoint block
-// Threads per galaxy team.  The library is built twice from the same sources: MAG_TEAM = 64
-// (libmagnetizer_b200.so: two points per thread on the default grid, nx = 107) and
-// MAG_TEAM = 128 (libmagnetizer_b200_team128.so, for grids of more than 256 points, e.g.
-// p_nx_ref = 401 of BASELINE config 5); mag_create of the first forwards to the second.
-#ifndef MAG_TEAM
-#define MAG_TEAM 32
-#endif
-#define MAG_FAST_MAXPPL 8     // fast path up to nx = 512
-#define MAG_LINE_S (4 * MAG_TEAM + 8)   // shared line of the PPL <= 4 variants
-#define MAG_LINE_L (8 * MAG_TEAM + 8)   // shared line of the PPL = 8 variant
+// Threads per galaxy team (template parameter TEAM of everything below).  k_evolve is
+// instantiated twice in the same library (mag_solver.cu): TEAM = 32 -- one warp per galaxy, the
+// register/shuffle loop of mag_rk_warp.cuh, highest throughput, used for the bulk of a batch --
+// and TEAM = 128 -- four warps per galaxy on the shared-line loop of this file (1 point per
+// thread on the default grid): the same work at a 4-5 times lower latency per Runge-Kutta
+// stage, used for the galaxies whose history is so long that one warp would still be busy with
+// it when the rest of the batch is done (the tail of the cost-ordered queue), and for grids the
+// warp loop does not take (p_nx_ref = 401 of BASELINE config 5).
+#define MAG_TEAM_LIGHT 32
+#define MAG_TEAM_HEAVY 128
+#define MAG_FAST_MAXPPL 8     // fast path up to nx = 8 * TEAM
+#define MAG_LINE_S(TEAM) (4 * (TEAM) + 8)   // shared line of the PPL <= 4 variants
+#define MAG_LINE_L(TEAM) (8 * (TEAM) + 8)   // shared line of the PPL = 8 variant
 // coefficient placement of a fast-loop variant
-#define COEF_REGS 0    // everything in registers (PPL = 2)
+#define COEF_REGS 0    // everything in registers (PPL = 1, 2)
 #define COEF_WSMEM 1   // 7+1 stencil weights in shared memory, the rest in registers (PPL = 3, 4)
 #define COEF_GLOBAL 2  // everything re-read from the team workspace (L1/L2) every stage (PPL = 8)
 
@@ -65,7 +68,8 @@ struct GuardK {
 };
 
 // per-team shared memory
-struct RkShared {
+template <int TEAM>
+struct RkSharedT {
   RngState rng;
   RngState rng_ck;                                        // checkpoint copy
   FastCall call;
@@ -76,12 +80,13 @@ struct RkShared {
   // (4 pad points each side, so that a thread's window -- own points +-3 -- is covered by
   // 16-byte aligned vector loads); for COEF_WSMEM the stencil weights [k][slot*64 + thread]
   // follow the short lines
-  alignas(16) double pool[(2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM) > 1920 ? (2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM) : 1920];
+  alignas(16) double pool[(2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM) > 1920 ? (2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM) : 1920];
+  static_assert(2 * 3 * MAG_LINE_L(TEAM) <= 2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM, "RkShared pool too small for the long lines");
 #ifdef MAG_WARP_SMEM_EXCHANGE
-  alignas(16) double xch[2][3][32 * 6];   // staged experiment (mag_rk_warp.cuh): halo exchange lines, 48-byte lane stride
+  alignas(16) double xch[2][3][32 * 6];   // build-time experiment (mag_rk_warp.cuh): halo exchange lines, 48-byte lane stride
 #endif
 };
-static_assert(2 * 3 * MAG_LINE_L <= 2 * 3 * MAG_LINE_S + 8 * 4 * MAG_TEAM, "RkShared pool too small for the long lines");
+using RkShared = RkSharedT<MAG_TEAM_LIGHT>;   // the one-warp loop of mag_rk_warp.cuh
 
 // update_floor_sign (floor_field.f90:99-114)
 __device__ __forceinline__ void update_floor_sign(Gal& G, double time) {
@@ -222,17 +227,17 @@ struct FastState {
   double kdc[MODE == COEF_GLOBAL ? 1 : PPL], p3[MODE == COEF_GLOBAL ? 1 : PPL], qc[MODE == COEF_GLOBAL ? 1 : PPL];
   double ak[MODE == COEF_GLOBAL ? 1 : PPL];
 };
-template <int PPL> struct LineLen { static constexpr int value = PPL <= 4 ? MAG_LINE_S : MAG_LINE_L; };
+template <int TEAM, int PPL> struct LineLen { static constexpr int value = PPL <= 4 ? MAG_LINE_S(TEAM) : MAG_LINE_L(TEAM); };
 
 // One Runge-Kutta stage.  STAGE: 0,1,2.  Reads the halo from line `buf`, updates f/ft in
 // registers, publishes the new state (boundary conditions applied) to the other line.
-template <int PPL, int MODE, int STAGE>
-__device__ __forceinline__ void fast_stage(FastState<PPL, MODE>& S, RkShared* rs, int tid, int buf, double dg, double dz,
+template <int TEAM, int PPL, int MODE, int STAGE>
+__device__ __forceinline__ void fast_stage(FastState<PPL, MODE>& S, RkSharedT<TEAM>* rs, int tid, int buf, double dg, double dz,
                                            double Rk, uint32_t pub_mask, uint32_t zero_mask, uint32_t mir_mask,
                                            uint32_t near_mask, const int* mir_addr, bool reload, unsigned& mB, unsigned& mA,
                                            unsigned& nB, unsigned& nA, double* alp_out, const double* W, int nxcap) {
-  constexpr int LL = LineLen<PPL>::value;
-  const double* wts = rs->pool + 2 * 3 * MAG_LINE_S;
+  constexpr int LL = LineLen<TEAM, PPL>::value;
+  const double* wts = rs->pool + 2 * 3 * MAG_LINE_S(TEAM);
   __syncthreads();
   // ---- gather the window: PPL own points + 3 halo points each side
   double win[3][PPL + 6];
@@ -262,8 +267,8 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, MODE>& S, RkShared* rs
     double w[7], w0a, c_ca, c_gs, c_fb, c_kdc, c_p3, c_qc, c_ak;
     if (MODE == COEF_WSMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) w[k] = wts[(k * 4 + j) * MAG_TEAM + tid];
-      w0a = wts[(7 * 4 + j) * MAG_TEAM + tid];
+      for (int k = 0; k < 7; k++) w[k] = wts[(k * 4 + j) * TEAM + tid];
+      w0a = wts[(7 * 4 + j) * TEAM + tid];
     } else if (MODE == COEF_REGS) {
 #pragma unroll
       for (int k = 0; k < 7; k++) w[k] = S.w[MODE == COEF_REGS ? j : 0][k];
@@ -348,16 +353,16 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, MODE>& S, RkShared* rs
 // Fast time loop of one snapshot attempt, executed by all 64 threads of the team.  G is the
 // leader warp's galaxy state (nullptr in the helper warp).  The result is left in rs->call
 // (ok, t, t_last_sign_choice, sign_nx, refresh_sign, point_stages) and in the workspace.
-template <int PPL, int MODE>
-__device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
-  constexpr int LL = LineLen<PPL>::value;
-  double* const wts = rs->pool + 2 * 3 * MAG_LINE_S;
+template <int TEAM, int PPL, int MODE>
+__device__ __noinline__ void fast_loop_team(Gal* G, RkSharedT<TEAM>* rs) {
+  constexpr int LL = LineLen<TEAM, PPL>::value;
+  double* const wts = rs->pool + 2 * 3 * MAG_LINE_S(TEAM);
   const int tid = threadIdx.x;
   const bool leader = tid < 32;
   const FastCall C = rs->call;
   double* const W = C.W;
   const int nxcap = C.nxcap, nx = C.nx, m = nx - MAG_NGHOST - 1, nsteps = C.nsteps;
-  const int npts = MAG_TEAM * PPL;
+  const int npts = TEAM * PPL;
   const double Rk = C.Rk, dt = C.dt;
   auto WA = [&](int id) { return W + (size_t)id * nxcap; };
 
@@ -408,8 +413,8 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
     const int g = tid * PPL + j;
     if (MODE == COEF_WSMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) wts[(k * 4 + j) * MAG_TEAM + tid] = WA(C_W0 + k)[g];
-      wts[(7 * 4 + j) * MAG_TEAM + tid] = WA(C_W0A)[g];
+      for (int k = 0; k < 7; k++) wts[(k * 4 + j) * TEAM + tid] = WA(C_W0 + k)[g];
+      wts[(7 * 4 + j) * TEAM + tid] = WA(C_W0A)[g];
     } else if (MODE == COEF_REGS) {
 #pragma unroll
       for (int k = 0; k < 7; k++) S.w[MODE == COEF_REGS ? j : 0][k] = WA(C_W0 + k)[g];
@@ -442,7 +447,7 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
   };
   // unused slots of both lines must read as (finite) zero
   __syncthreads();   // (the weights above live behind the short lines; the long lines overlap them)
-  for (int i = tid; i < 2 * 3 * LL; i += MAG_TEAM) rs->pool[i] = 0.0;
+  for (int i = tid; i < 2 * 3 * LL; i += TEAM) rs->pool[i] = 0.0;
   __syncthreads();
 
   const double dg0 = dt * (8.0 / 15), dg1 = dt * (5.0 / 12), dg2 = dt * (3.0 / 4);
@@ -508,11 +513,11 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
         load_signed_floor();
       }
       double* alp_out = (jt + s == nsteps) ? WA(A_ALP) : nullptr;
-      fast_stage<PPL, MODE, 0>(S, rs, tid, buf, dg0, dz0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr, W, nxcap);
+      fast_stage<TEAM, PPL, MODE, 0>(S, rs, tid, buf, dg0, dz0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr, W, nxcap);
       buf ^= 1;
-      fast_stage<PPL, MODE, 1>(S, rs, tid, buf, dg1, dz1, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr, W, nxcap);
+      fast_stage<TEAM, PPL, MODE, 1>(S, rs, tid, buf, dg1, dz1, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, nullptr, W, nxcap);
       buf ^= 1;
-      fast_stage<PPL, MODE, 2>(S, rs, tid, buf, dg2, 0.0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, alp_out, W, nxcap);
+      fast_stage<TEAM, PPL, MODE, 2>(S, rs, tid, buf, dg2, 0.0, Rk, pub_mask, zero_mask, mir_mask, near_mask, mir_addr, reload, mB, mA, nB, nA, alp_out, W, nxcap);
       buf ^= 1;
       // t = t + dt*gam1 ; ttmp = t + dt*zet1 ; t = ttmp + dt*gam2 ; ttmp = t + dt*zet2 ; t = ttmp + dt*gam3
       double tt = t + dg0;
@@ -597,39 +602,40 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkShared* rs) {
 }
 
 }  // namespace magdev
-#if MAG_TEAM == 32
 #include "mag_rk_warp.cuh"
-#endif
 namespace magdev {
 
-__device__ __forceinline__ void fast_dispatch(Gal* G, RkShared* rs) {
+template <int TEAM>
+__device__ __forceinline__ void fast_dispatch(Gal* G, RkSharedT<TEAM>* rs) {
   switch (rs->call.ppl) {
-    case 2: fast_loop_team<2, COEF_REGS>(G, rs); break;
-    case 3: fast_loop_team<3, COEF_WSMEM>(G, rs); break;
-    case 4: fast_loop_team<4, COEF_WSMEM>(G, rs); break;
-    default: fast_loop_team<8, COEF_GLOBAL>(G, rs); break;
+    case 1: if (TEAM > 32) fast_loop_team<TEAM, 1, COEF_REGS>(G, rs); break;   // (one-warp teams: nx >= 64 has PPL >= 2)
+    case 2: fast_loop_team<TEAM, 2, COEF_REGS>(G, rs); break;
+    case 3: fast_loop_team<TEAM, 3, COEF_WSMEM>(G, rs); break;
+    case 4: fast_loop_team<TEAM, 4, COEF_WSMEM>(G, rs); break;
+    default: fast_loop_team<TEAM, 8, COEF_GLOBAL>(G, rs); break;
   }
 }
 
 // Leader warp: runs the time loop of the current snapshot attempt.  Returns ok (false: the
 // field blew up, check_f_error).
-__device__ bool run_timesteps(Gal& G, RkShared* rs) {
+template <int TEAM>
+__device__ bool run_timesteps(Gal& G, RkSharedT<TEAM>* rs) {
   if (G.nsteps < 1) return true;
-#if MAG_TEAM == 32
-  if (G.a->use_fast && warp_path_applies(G)) return warp_dispatch(G, rs);
-#endif
-  if (G.a->use_fast && G.nx >= 32 && G.nx <= MAG_FAST_MAXPPL * MAG_TEAM) {
+  if (TEAM == MAG_TEAM_LIGHT) {
+    if (G.a->use_fast && warp_path_applies(G)) return warp_dispatch(G, reinterpret_cast<RkShared*>(rs));
+  }
+  if (G.a->use_fast && G.nx >= 32 && G.nx <= MAG_FAST_MAXPPL * TEAM) {
     if (G.lane == 0) {
       FastCall& C = rs->call;
       C.W = G.W; C.nxcap = G.a->nxcap; C.nx = G.nx; C.nsteps = G.nsteps;
-      C.ppl = G.nx <= 2 * MAG_TEAM ? 2 : (G.nx <= 3 * MAG_TEAM ? 3 : (G.nx <= 4 * MAG_TEAM ? 4 : 8));
+      C.ppl = (TEAM > 32 && G.nx <= TEAM) ? 1 : (G.nx <= 2 * TEAM ? 2 : (G.nx <= 3 * TEAM ? 3 : (G.nx <= 4 * TEAM ? 4 : 8)));
       C.sign_nx = G.sign_nx; C.refresh_sign = G.refresh_sign ? 1 : 0; C.cmd = TEAM_CMD_FAST; C.ok = 1;
       C.dt = G.dt; C.t = G.t; C.t_Gyr = G.t_Gyr; C.dtg = G.dt * G.a->U.t0_Gyr;
       C.tau_min_kappa = G.a->P.p_floor_kappa * G.tau_min; C.t_last_sign_choice = G.t_last_sign_choice;
       C.Rk = G.a->P.R_kappa; C.point_stages = 0;
     }
-    __syncthreads();   // releases the helper warp (k_evolve)
-    fast_dispatch(&G, rs);
+    __syncthreads();   // releases the helper warps (k_evolve)
+    fast_dispatch<TEAM>(&G, rs);
     const FastCall& C = rs->call;
     G.t = C.t; G.t_last_sign_choice = C.t_last_sign_choice; G.refresh_sign = C.refresh_sign != 0; G.sign_nx = C.sign_nx;
     G.point_stages += C.point_stages;

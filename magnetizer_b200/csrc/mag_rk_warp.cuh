@@ -218,16 +218,7 @@ __device__ __forceinline__ void warp_ghosts(WarpState<PPL, MODE>& S, const int l
       case 6: if (PPL > 6) outer_ghosts<PPL, MODE, (PPL > 6 ? 6 : 0)>(S, lane, tm); break;
       case 7: if (PPL > 7) outer_ghosts<PPL, MODE, (PPL > 7 ? 7 : 0)>(S, lane, tm); break;
       case 8: if (PPL > 8) outer_ghosts<PPL, MODE, (PPL > 8 ? 8 : 0)>(S, lane, tm); break;
-#ifdef MAG_WARP_PPL16
-      case 9: if (PPL > 9) outer_ghosts<PPL, MODE, (PPL > 9 ? 9 : 0)>(S, lane, tm); break;
-      case 10: if (PPL > 10) outer_ghosts<PPL, MODE, (PPL > 10 ? 10 : 0)>(S, lane, tm); break;
-      case 11: if (PPL > 11) outer_ghosts<PPL, MODE, (PPL > 11 ? 11 : 0)>(S, lane, tm); break;
-      case 12: if (PPL > 12) outer_ghosts<PPL, MODE, (PPL > 12 ? 12 : 0)>(S, lane, tm); break;
-      case 13: if (PPL > 13) outer_ghosts<PPL, MODE, (PPL > 13 ? 13 : 0)>(S, lane, tm); break;
-      default: if (PPL > 14) outer_ghosts<PPL, MODE, (PPL > 14 ? 14 : 0)>(S, lane, tm); break;
-#else
       default: if (PPL > 9) outer_ghosts<PPL, MODE, (PPL > 9 ? 9 : 0)>(S, lane, tm); break;
-#endif
     }
   }
 }
@@ -700,13 +691,8 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
 // fall into a lane (slots up to P+4 < 32*PPL); 0 if the warp path does not take this grid.
 __device__ __forceinline__ int warp_ppl(int nx) {
   const int P = nx - 2 * MAG_NGHOST - 1;
-#ifdef MAG_WARP_PPL16   // staged for the next round (not validated on the GPU): grids up to 505 points
-  const int cand[6] = {4, 5, 6, 8, 11, 16};
-  const int ncand = 6;
-#else
   const int cand[5] = {4, 5, 6, 8, 11};
   const int ncand = 5;
-#endif
   for (int c = 0; c < ncand; c++)
     if (P + WARP_J0 + 3 < 32 * cand[c]) return cand[c];
   return 0;
@@ -727,9 +713,6 @@ __device__ __forceinline__ bool warp_dispatch(Gal& G, RkShared* rs) {
     case 5: return warp_loop<5, WM_WSM, -1>(G, rs);
     case 6: return warp_loop<6, WM_WSM2, -1>(G, rs);
     case 8: return warp_loop<8, WM_ALLG, -1>(G, rs);
-#ifdef MAG_WARP_PPL16
-    case 16: return warp_loop<16, WM_ALLG, -1>(G, rs);
-#endif
     default: return warp_loop<11, WM_ALLG, -1>(G, rs);
   }
 }

@@ -1,18 +1,22 @@
-// mag_solver.cu -- persistent warp-per-galaxy kernel and the C ABI (include/magnetizer_b200.h).
+// mag_solver.cu -- persistent team-per-galaxy kernels and the single-GPU C ABI
+// (include/magnetizer_b200.h).
 //
 // Replaces, for the per-galaxy dynamo path only, the reference's MPI master/worker farm
 // (source/distributor.f90:253-384) + work routine dynamo_run (source/dynamo.f90:39): the
-// farm becomes a device-side work queue (one atomic counter) drained by persistent warps,
-// each of which runs a whole galaxy history.  No collective, no host round trip between
+// farm becomes device-side work queues (atomic counters) drained by persistent teams, each
+// of which runs a whole galaxy history.  No collective, no host round trip between
 // snapshots; inputs are staged into HBM once per batch and read with coalesced loads
 // (snapshot index fastest), outputs are written as contiguous 101-point rows.
+//
+// One solve = k_profiles (+ k_chains + k_profiles) -> cost sort -> k_evolve_heavy || k_evolve:
+// the galaxies whose history is longer than a warp slot's fair share of the batch (the tail
+// of a longest-first schedule) run on four-warp teams at a 4-5 times lower latency per
+// Runge-Kutta stage, everything else on one warp per galaxy (highest throughput).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
-
-#include <dlfcn.h>
 
 #include "mag_galaxy.cuh"
 #include "mag_phases.cuh"
@@ -25,11 +29,10 @@ using namespace magdev;
 #define MAG_PROFILE_MAXREG 128   // 16 warps per SM: the profile phase is latency bound (serial root-finder chains)
 #endif
 #ifndef MAG_EVOLVE_MAXREG
-#if MAG_TEAM == 32
-#define MAG_EVOLVE_MAXREG 255   // 8 one-warp teams per SM, everything of a galaxy in registers
-#else
-#define MAG_EVOLVE_MAXREG 168
+#define MAG_EVOLVE_MAXREG 255    // 8 one-warp teams per SM, everything of a galaxy in registers
 #endif
+#ifndef MAG_HEAVY_MAXREG
+#define MAG_HEAVY_MAXREG 168     // 3 four-warp teams per SM
 #endif
 
 static thread_local std::string g_last_error;
@@ -70,11 +73,12 @@ __global__ void __maxnreg__(MAG_PROFILE_MAXREG) k_profiles(KernelArgs a) {
     }
     if (lane == 0 && a.chain_mode != CHAIN_MODE_EXPORT) {
       a.heads[q] = H;
-      if (a.out.error) a.out.error[G.g] = H.error;
+      if (H.cost > 0) atomicAdd(a.cost_total, (unsigned long long)H.cost);
+      if (a.o_error) a.o_error[G.g] = H.error;
       if (err) {  // nothing else is written for this galaxy (dynamo.f90:69-73)
-        if (a.out.nsteps) a.out.nsteps[G.g] = G.nsteps;
-        if (a.out.point_stages) a.out.point_stages[G.g] = 0;
-        if (a.out.flags) a.out.flags[G.g] = G.flags;
+        if (a.o_nsteps) a.o_nsteps[G.g] = G.nsteps;
+        if (a.o_point_stages) a.o_point_stages[G.g] = 0;
+        if (a.o_flags) a.o_flags[G.g] = G.flags;
       }
     }
     __syncwarp();
@@ -89,68 +93,116 @@ __global__ void __launch_bounds__(128) k_chains(KernelArgs a) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) run_chain_job(a, j);
 }
 
-// ------------------------------------------------------------------ Phase B kernel
-// One team of MAG_TEAM threads per galaxy, persistent, longest history first.  MAG_TEAM = 32
-// (default build): the team is ONE warp that does everything, the time loop in registers with
-// shuffles (mag_rk_warp.cuh).  MAG_TEAM = 128 (grids of more than 256 points): warp 0 leads
-// (seeds, grid transformations of f, outputs, generic path), the helper warps join for the
-// shared-line time loop (mag_rk_fast.cuh).
+// ------------------------------------------------------------------ Phase B kernels
+// Light class: one warp per galaxy, persistent, longest history first; the warp does
+// everything, the time loop in registers with shuffles (mag_rk_warp.cuh).  The queue of this
+// class starts behind the heavy entries of `order`.
 __global__ void __maxnreg__(MAG_EVOLVE_MAXREG) k_evolve(KernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RkShared* rs = reinterpret_cast<RkShared*>(smem_raw);
+  RkSharedT<MAG_TEAM_LIGHT>* rs = reinterpret_cast<RkSharedT<MAG_TEAM_LIGHT>*>(smem_raw);
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x >= 32) {  // helper warps (MAG_TEAM > 32 only)
-    for (;;) {
-      __syncthreads();
-      if (rs->call.cmd == TEAM_CMD_EXIT) break;
-      fast_dispatch(nullptr, rs);
-    }
-    return;
-  }
   Gal G;
   G.a = &a;
   G.W = a.ws2 + (size_t)blockIdx.x * A_COUNT * a.nxcap;
   G.rng = &rs->rng;
   G.lane = lane;
+  const int nh = *a.n_heavy, n = a.g1 - a.g0;
   for (;;) {
     int q = 0;
-    if (lane == 0) q = atomicAdd(a.counter2, 1);
+    if (lane == 0) q = nh + atomicAdd(a.counter2, 1);
     q = __shfl_sync(FULL, q, 0);
-    if (q >= a.g1 - a.g0) break;
+    if (q >= n) break;
     const int qi = a.order[q];
     const GalHead H = a.heads[qi];
     if (H.error) continue;
     G.g = a.g0 + qi;
-    run_evolve(G, H, rs);
+    run_evolve<MAG_TEAM_LIGHT>(G, H, rs);
+  }
+  // launched as the programmatic dependent of k_evolve_heavy (which it does not depend on): the
+  // stream must not run ahead of the heavy teams, so one CTA joins them before the grid retires
+  if (a.pdl_join && blockIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Heavy class: four warps per galaxy.  Warp 0 leads (seeds, grid transformations of f, outputs,
+// generic path), the helper warps join for the shared-line time loop (mag_rk_fast.cuh).
+__global__ void __maxnreg__(MAG_HEAVY_MAXREG) k_evolve_heavy(KernelArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;");   // the light kernel may start filling the free SMs at once
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RkSharedT<MAG_TEAM_HEAVY>* rs = reinterpret_cast<RkSharedT<MAG_TEAM_HEAVY>*>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32) {  // helper warps
+    for (;;) {
+      __syncthreads();
+      if (rs->call.cmd == TEAM_CMD_EXIT) break;
+      fast_dispatch<MAG_TEAM_HEAVY>(nullptr, rs);
+    }
+    return;
+  }
+  Gal G;
+  G.a = &a;
+  G.W = a.ws3 + (size_t)blockIdx.x * A_COUNT * a.nxcap;
+  G.rng = &rs->rng;
+  G.lane = lane;
+  const int nh = *a.n_heavy;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(a.counter3, 1);
+    q = __shfl_sync(FULL, q, 0);
+    if (q >= nh) break;
+    const int qi = a.order[q];
+    const GalHead H = a.heads[qi];
+    if (H.error) continue;
+    G.g = a.g0 + qi;
+    run_evolve<MAG_TEAM_HEAVY>(G, H, rs);
   }
   if (lane == 0) rs->call.cmd = TEAM_CMD_EXIT;
   __syncthreads();
 }
 
-// ------------------------------------------------------------------ cost-ordered queue
-// Longest histories first (exact cost = sum of nsteps*nx known after Phase A): a counting
-// sort on 1/16-octave buckets of the cost.
+// ------------------------------------------------------------------ cost-ordered queues
+// Exact cost = sum of nsteps*nx, known after Phase A.  `order` = heavy class first, then the
+// light class, each longest-first (counting sort on 1/16-octave buckets of the cost).  A
+// galaxy is heavy when its history alone would keep one warp busy for longer than `alpha`
+// times the fair share of a warp slot (sum of all costs / number of slots): under a
+// longest-first schedule those are the galaxies that end up as the tail.  Grids the one-warp
+// loop does not take (nx_max > nx_heavy) are heavy as well.
 #define COST_BUCKETS 1024
+struct QueuePolicy {
+  int mode;        // 0: everything light, 1: by cost, 2: everything heavy
+  int nx_heavy;
+  double alpha_over_slots;
+};
 __device__ __forceinline__ int cost_bucket(long long c) {
   if (c <= 0) return 0;
   const int b = (int)(log2f((float)c) * 16.0f) + 1;
   return b >= COST_BUCKETS ? COST_BUCKETS - 1 : b;
 }
-__global__ void k_cost_hist(const GalHead* heads, int n, int* hist) {
+__device__ __forceinline__ int queue_slot(const GalHead& h, const QueuePolicy& p, unsigned long long total) {
+  bool heavy = false;
+  if (!h.error && h.cost > 0) {
+    if (p.mode == 2) heavy = true;
+    else if (p.mode == 1) heavy = (double)h.cost > p.alpha_over_slots * (double)total || h.nx_max > p.nx_heavy;
+  }
+  return (heavy ? 0 : COST_BUCKETS) + (COST_BUCKETS - 1 - cost_bucket(h.cost));   // ascending slot = descending cost
+}
+__global__ void k_cost_hist(const GalHead* heads, int n, int* hist, QueuePolicy p, const unsigned long long* total) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  atomicAdd(&hist[cost_bucket(heads[i].cost)], 1);
+  atomicAdd(&hist[queue_slot(heads[i], p, *total)], 1);
 }
-__global__ void k_cost_scan(int* hist) {  // descending exclusive scan, in place
+__global__ void k_cost_scan(int* hist, int* n_heavy) {  // exclusive scan, in place
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
-    for (int k = COST_BUCKETS - 1; k >= 0; k--) { int c = hist[k]; hist[k] = acc; acc += c; }
+    for (int k = 0; k < 2 * COST_BUCKETS; k++) {
+      if (k == COST_BUCKETS) *n_heavy = acc;
+      int c = hist[k]; hist[k] = acc; acc += c;
+    }
   }
 }
-__global__ void k_cost_scatter(const GalHead* heads, int n, int* hist, int* order) {
+__global__ void k_cost_scatter(const GalHead* heads, int n, int* hist, int* order, QueuePolicy p, const unsigned long long* total) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  order[atomicAdd(&hist[cost_bucket(heads[i].cost)], 1)] = i;
+  order[atomicAdd(&hist[queue_slot(heads[i], p, *total)], 1)] = i;
 }
 
 // FP64 peak micro-benchmark: independent DFMA chains, 2 flops each
@@ -165,17 +217,36 @@ __global__ void k_dfma_peak(double* out, int iters) {
 }
 
 // ------------------------------------------------------------------ host side
+// device-side counters of one context (one int each)
+enum Counter { CNT_A = 0, CNT_FAIL, CNT_REPLAYS, CNT_LIGHT, CNT_HEAVY, CNT_NHEAVY, CNT_INVALIDATED, CNT_NHEAVY_SUM, CNT_COUNT };
+
+// one solve of the host-buffer API, kept until mag_wait (and for a retry with a larger arena)
+struct PendingCall {
+  bool active = false;
+  int32_t ngal_total = 0, g0 = 0, n = 0, nz = 0;
+  const int32_t* gal_ids = nullptr;
+  const double* t_gyr = nullptr;
+  const double* inputs = nullptr;
+  int32_t n_profile_q = 0, n_scalar_q = 0;
+  int32_t profile_q[MAG_NPROFILE], scalar_q[MAG_NSCALAR];
+  mag_outputs_t out;
+  // planes of the profile phase that were staged in HBM and copied out while k_evolve was running
+  int n_early = 0;
+  struct { double* dev; double* host; size_t bytes; } early[MAG_NPROFILE];
+};
+
 struct mag_ctx {
   mag_params_t P;
   int device = 0;
   int sm_count = 0;
-  int ctasA_per_sm = 0, ctasB_per_sm = 0;
-  int nwarpsA = 0, nteamsB = 0;
+  int ctasA_per_sm = 0, ctasB_per_sm = 0, ctasH_per_sm = 0;
+  int nwarpsA = 0, nteamsB = 0, nteamsH = 0;
   int nxcap = 0;
   double* wsA = nullptr;      // Phase A: per-warp workspaces
-  double* wsB = nullptr;      // Phase B: per-team workspaces
-  int* d_counter = nullptr;   // [0] A queue head, [1] fail flag, [2] fast-path replays, [3] B queue head
-  unsigned long long* d_arena_top = nullptr;
+  double* wsB = nullptr;      // Phase B: per-team workspaces, one-warp teams
+  double* wsH = nullptr;      // Phase B: four-warp teams
+  int* d_counter = nullptr;   // [CNT_COUNT]
+  unsigned long long* d_arena_top = nullptr;   // [0] arena top, [1] cost total of the chunk
   int* d_hist = nullptr;
   int* d_order = nullptr;
   ChainJob* d_jobs = nullptr;
@@ -188,62 +259,29 @@ struct mag_ctx {
   int nz_cap = 0;
   double* d_arena = nullptr;
   long long arena_cap = 0;    // doubles
+  int nx_budget_pct = 165;    // arena budget per snapshot in percent of the default grid
   // staging for the host-buffer API
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* h_status = nullptr;    // pinned: fail flag, n_invalidated, replays, heavy galaxies of the last call
+  cudaStream_t stream = nullptr, stream_h = nullptr, stream_copy = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prof = nullptr, ev_copy = nullptr;
   double last_ms[4] = {0, 0, 0, 0};
   int last_launches = 0;
-  int last_replays = 0;
   int use_fast = 1;
-  // forwarding to the MAG_TEAM = 128 build of this library for grids of more than 256 points
-  void* fwd_lib = nullptr;
-  mag_ctx* fwd_ctx = nullptr;
+  int launch_pdl = 0;         // 1: light kernel as programmatic dependent of the heavy one, 0: two streams
+  int stage_profile_rows = 1; // rows of the profile phase: HBM + one copy per plane during k_evolve (0: zero-copy stores)
+  QueuePolicy policy;
+  double heavy_alpha = 0.6;
+  PendingCall pend;
 };
 
-#if MAG_TEAM == 32
-namespace {
-struct FwdApi {
-  int (*create)(const mag_params_t*, int, mag_ctx_t**);
-  void (*destroy)(mag_ctx_t*);
-  int (*solve)(mag_ctx_t*, int32_t, const int32_t*, int32_t, const double*, const double*, int32_t, const int32_t*, int32_t,
-               const int32_t*, const mag_outputs_t*);
-  int (*solve_dev)(mag_ctx_t*, int32_t, const int32_t*, int32_t, const double*, const double*, int32_t, const int32_t*, int32_t,
-                   const int32_t*, const mag_outputs_t*, void*);
-  int (*timing)(mag_ctx_t*, double*);
-  double (*peak)(mag_ctx_t*, int);
-  int (*info)(mag_ctx_t*, int32_t*);
-  int (*set_fast)(mag_ctx_t*, int32_t);
-  const char* (*last_error)(void);
-};
-FwdApi g_fwd;
-void* open_big_team_library() {
-  Dl_info di;
-  if (!dladdr((void*)&open_big_team_library, &di) || !di.dli_fname) return nullptr;
-  std::string path(di.dli_fname);
-  const size_t slash = path.rfind('/');
-  path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/libmagnetizer_b200_team128.so";
-  void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
-  if (!h) return nullptr;
-  g_fwd.create = (decltype(g_fwd.create))dlsym(h, "mag_create");
-  g_fwd.destroy = (decltype(g_fwd.destroy))dlsym(h, "mag_destroy");
-  g_fwd.solve = (decltype(g_fwd.solve))dlsym(h, "mag_solve_batch");
-  g_fwd.solve_dev = (decltype(g_fwd.solve_dev))dlsym(h, "mag_solve_batch_device");
-  g_fwd.timing = (decltype(g_fwd.timing))dlsym(h, "mag_last_timing");
-  g_fwd.peak = (decltype(g_fwd.peak))dlsym(h, "mag_measure_fp64_peak");
-  g_fwd.info = (decltype(g_fwd.info))dlsym(h, "mag_ctx_info");
-  g_fwd.set_fast = (decltype(g_fwd.set_fast))dlsym(h, "mag_set_fast_path");
-  g_fwd.last_error = (decltype(g_fwd.last_error))dlsym(h, "mag_last_error");
-  if (!g_fwd.create || !g_fwd.destroy || !g_fwd.solve || !g_fwd.solve_dev || !g_fwd.timing || !g_fwd.peak || !g_fwd.info ||
-      !g_fwd.set_fast || !g_fwd.last_error) { dlclose(h); return nullptr; }
-  return h;
+// virtual base of an array whose first row belongs to catalogue galaxy g_first (see KernelArgs)
+template <class T>
+static T* vbase(T* real, long long g_first, size_t row_elems) {
+  return real ? real - (ptrdiff_t)(g_first * (long long)row_elems) : nullptr;
 }
-}  // namespace
-#define MAG_FWD(c, call) if ((c) && (c)->fwd_ctx) return call
-#else
-#define MAG_FWD(c, call)
-#endif
 
 extern "C" {
 
@@ -273,7 +311,10 @@ void mag_params_default(mag_params_t* p) {
   p->p_variable_timesteps = 1; p->p_simplified_pressure = 1; p->p_halo_contraction = 1; p->p_enable_P2 = 0;
   p->Dyn_quench = 1; p->Alg_quench = 0; p->Damp = 0; p->lFloor = 1;
   p->p_space_varying_floor = 1; p->p_time_varying_floor = 1; p->p_limit_turbulent_scale = 1;
-  p->p_allow_positive_shears = 0; p->seed_choice = 0; p->outflow_type = 0;
+  p->p_allow_positive_shears = 0; p->seed_choice = 0; p->outflow_type = MAG_OUTFLOW_NONE;
+  // outflow_parameters (global_input_parameters.f90:303-325)
+  p->p_outflow_Lsn = 1e38; p->p_outflow_fOB = (double)0.7f; p->p_outflow_etaSN = 9.4e-3; p->p_tOB = 3.0; p->p_N_SN1OB = 40.0;
+  p->p_outflow_hot_gas_density = 1.7e-27; p->p_outflow_nu0 = 0.5; p->p_outflow_alphahot = (double)-3.2f; p->p_outflow_Vhot = 425.0;
 }
 
 static bool params_supported(const mag_params_t& p) {
@@ -281,8 +322,80 @@ static bool params_supported(const mag_params_t& p) {
          p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && p.Alg_quench == 0 && p.Damp == 0 &&
          p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
          p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice == 0 &&
-         p.outflow_type == 0 && p.p_nx_ref >= 8 && (p.rng_kind == 0 || p.rng_kind == 1) &&
-         p.p_nx_MAX >= p.p_nx_ref + 6;
+         p.outflow_type >= MAG_OUTFLOW_NONE && p.outflow_type <= MAG_OUTFLOW_SUPERBUBBLE && p.p_nx_ref >= 8 &&
+         (p.rng_kind == 0 || p.rng_kind == 1) && p.p_nx_MAX >= p.p_nx_ref + 6;
+}
+
+void mag_destroy(mag_ctx_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->wsA); cudaFree(c->wsB); cudaFree(c->wsH); cudaFree(c->d_counter); cudaFree(c->d_arena_top); cudaFree(c->d_hist);
+  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena);
+  cudaFree(c->d_jobs); cudaFree(c->d_jobidx); cudaFree(c->d_job_count);
+  cudaFree(c->d_stage);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_prof, c->ev_copy}) if (e) cudaEventDestroy(e);
+  for (cudaStream_t s : {c->stream, c->stream_h, c->stream_copy}) if (s) cudaStreamDestroy(s);
+  delete c;
+}
+
+static int create_impl(mag_ctx* c, const cudaDeviceProp& prop) {
+  const mag_params_t* params = &c->P;
+  c->sm_count = prop.multiProcessorCount;
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
+  c->split_chains = env_int("MAG_INLINE_CHAINS", 0) ? 0 : 1;
+  c->use_fast = env_int("MAG_DISABLE_FAST_PATH", 0) ? 0 : 1;
+  c->launch_pdl = env_int("MAG_EVOLVE_PDL", 0);
+  c->stage_profile_rows = env_int("MAG_STAGE_PROFILE_ROWS", 1);
+  c->policy.mode = env_int("MAG_HEAVY_MODE", 1);
+  c->policy.nx_heavy = env_int("MAG_HEAVY_NX", 352);
+  c->nx_budget_pct = env_int("MAG_ARENA_NX_PCT", 165);
+  if (const char* e = getenv("MAG_HEAVY_ALPHA")) c->heavy_alpha = atof(e);
+  const size_t smemB = sizeof(RkSharedT<MAG_TEAM_LIGHT>), smemH = sizeof(RkSharedT<MAG_TEAM_HEAVY>);
+  CUDA_TRY(cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+  CUDA_TRY(cudaFuncSetAttribute(k_evolve_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
+  int occA = 0, occB = 0, occH = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, k_profiles, WARPS_PER_CTA * 32, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_evolve, MAG_TEAM_LIGHT, smemB));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occH, k_evolve_heavy, MAG_TEAM_HEAVY, smemH));
+  if (occA < 1 || occB < 1 || occH < 1) { set_error("kernel does not fit on an SM"); return MAG_ERR_CUDA; }
+  c->ctasA_per_sm = occA; c->ctasB_per_sm = occB; c->ctasH_per_sm = occH;
+  c->nwarpsA = c->sm_count * occA * WARPS_PER_CTA;
+  c->nteamsB = c->sm_count * occB;
+  c->nteamsH = c->sm_count * occH;
+  c->policy.alpha_over_slots = c->heavy_alpha / (double)c->nteamsB;
+  int cap = env_int("MAG_NXCAP", 2048);
+  if (cap > params->p_nx_MAX) cap = params->p_nx_MAX;
+  if (cap < params->p_nx_ref + 6) cap = params->p_nx_ref + 6;
+  if (cap < 1024) cap = 1024;   // the team loops address up to 8 points per thread; room for the pair table of the large-grid warp variants
+  c->nxcap = (cap + 15) & ~15;
+  const size_t per_team = (size_t)A_COUNT * c->nxcap * sizeof(double);
+  CUDA_TRY(cudaMalloc(&c->wsA, c->nwarpsA * per_team));
+  CUDA_TRY(cudaMemset(c->wsA, 0, c->nwarpsA * per_team));
+  CUDA_TRY(cudaMalloc(&c->wsB, c->nteamsB * per_team));
+  CUDA_TRY(cudaMemset(c->wsB, 0, c->nteamsB * per_team));
+  CUDA_TRY(cudaMalloc(&c->wsH, c->nteamsH * per_team));
+  CUDA_TRY(cudaMemset(c->wsH, 0, c->nteamsH * per_team));
+  CUDA_TRY(cudaMalloc(&c->d_counter, CNT_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMemset(c->d_counter, 0, CNT_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_arena_top, 2 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&c->d_hist, 2 * COST_BUCKETS * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&c->d_job_count, sizeof(int)));
+  CUDA_TRY(cudaHostAlloc(&c->h_status, 8 * sizeof(int), cudaHostAllocDefault));
+  memset(c->h_status, 0, 8 * sizeof(int));
+  int prio_lo = 0, prio_hi = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_h, cudaStreamNonBlocking, prio_hi));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_prof, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+  return MAG_OK;
 }
 
 int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
@@ -298,74 +411,13 @@ int mag_create(const mag_params_t* params, int device, mag_ctx_t** ctx_out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) { set_error("kernels are built for sm_100a only"); return MAG_ERR_NO_DEVICE; }
-#if MAG_TEAM == 32
-  if (params->p_nx_ref + 2 * MAG_NGHOST > 256) {
-    // more than 256 grid points: use the 128-thread-team build if it is there (same ABI)
-    if (void* h = open_big_team_library()) {
-      mag_ctx* w = new mag_ctx();
-      w->P = *params; w->device = device; w->fwd_lib = h;
-      const int rc = g_fwd.create(params, device, &w->fwd_ctx);
-      if (rc != MAG_OK) { set_error(g_fwd.last_error()); delete w; return rc; }
-      *ctx_out = w;
-      return MAG_OK;
-    }
-  }
-#endif
   mag_ctx* c = new mag_ctx();
   c->P = *params;
   c->device = device;
-  c->sm_count = prop.multiProcessorCount;
-  const char* env_split = getenv("MAG_INLINE_CHAINS");
-  c->split_chains = (env_split && env_split[0] == '1') ? 0 : 1;
-  const char* env_fast = getenv("MAG_DISABLE_FAST_PATH");
-  c->use_fast = (env_fast && env_fast[0] == '1') ? 0 : 1;
-  const size_t smemB = sizeof(RkShared);
-  CUDA_TRY(cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-  int occA = 0, occB = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, k_profiles, WARPS_PER_CTA * 32, 0));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, k_evolve, MAG_TEAM, smemB));
-  if (occA < 1 || occB < 1) { set_error("kernel does not fit on an SM"); delete c; return MAG_ERR_CUDA; }
-  c->ctasA_per_sm = occA; c->ctasB_per_sm = occB;
-  c->nwarpsA = c->sm_count * occA * WARPS_PER_CTA;
-  c->nteamsB = c->sm_count * occB;
-  const char* env_cap = getenv("MAG_NXCAP");
-  int cap = env_cap ? atoi(env_cap) : 2048;
-  if (cap > params->p_nx_MAX) cap = params->p_nx_MAX;
-  if (cap < params->p_nx_ref + 6) cap = params->p_nx_ref + 6;
-  if (cap < MAG_FAST_MAXPPL * MAG_TEAM) cap = MAG_FAST_MAXPPL * MAG_TEAM;  // the fast path addresses up to 256 points
-#if MAG_TEAM == 32
-  if (cap < 1024) cap = 1024;   // room for the coefficient pair table of the large-grid warp variants (mag_rk_warp.cuh)
-#endif
-  c->nxcap = (cap + 15) & ~15;
-  const size_t wsA = (size_t)c->nwarpsA * A_COUNT * c->nxcap * sizeof(double);
-  const size_t wsB = (size_t)c->nteamsB * A_COUNT * c->nxcap * sizeof(double);
-  CUDA_TRY(cudaMalloc(&c->wsA, wsA));
-  CUDA_TRY(cudaMemset(c->wsA, 0, wsA));
-  CUDA_TRY(cudaMalloc(&c->wsB, wsB));
-  CUDA_TRY(cudaMemset(c->wsB, 0, wsB));
-  CUDA_TRY(cudaMalloc(&c->d_counter, 4 * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&c->d_arena_top, sizeof(unsigned long long)));
-  CUDA_TRY(cudaMalloc(&c->d_hist, COST_BUCKETS * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&c->d_job_count, sizeof(int)));
-  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+  const int rc = create_impl(c, prop);
+  if (rc != MAG_OK) { const std::string msg = g_last_error; mag_destroy(c); set_error(msg); return rc; }   // nothing leaks on a failed create
   *ctx_out = c;
   return MAG_OK;
-}
-
-void mag_destroy(mag_ctx_t* c) {
-  if (!c) return;
-#if MAG_TEAM == 32
-  if (c->fwd_ctx) { g_fwd.destroy(c->fwd_ctx); delete c; return; }
-#endif
-  cudaSetDevice(c->device);
-  cudaFree(c->wsA); cudaFree(c->wsB); cudaFree(c->d_counter); cudaFree(c->d_arena_top); cudaFree(c->d_hist);
-  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena);
-  cudaFree(c->d_jobs); cudaFree(c->d_jobidx); cudaFree(c->d_job_count);
-  cudaFree(c->d_stage);
-  for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  if (c->stream) cudaStreamDestroy(c->stream);
-  delete c;
 }
 
 static int check_quantities(int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q, const int32_t* scalar_q) {
@@ -376,16 +428,20 @@ static int check_quantities(int32_t n_profile_q, const int32_t* profile_q, int32
 }
 
 // Record storage: SnapRec/GalHead tables for `chunk` galaxies and an arena for their arrays.
-// The arena budget per snapshot is R_COUNT arrays of ARENA_NX_BUDGET points (default grid
-// 107; grid extensions reach ~330 in the example input but are rare); a batch that does not
-// fit is solved in several chunks, and a chunk that overflows the arena is reported as
-// MAG_ERR_CUDA with an explanatory message.
+// The arena budget per snapshot is ARENA_ARRAYS arrays of nx_budget points (1.65 x the default
+// grid; grid extensions reach 3 x nx in the example input but only for ~1 % of the snapshots).
+// A range that does not fit is solved in several chunks; a chunk that overflows the arena
+// raises MAG_ERR_ARENA on the device and mag_wait repeats the solve with twice the budget.
 #define ARENA_ARRAYS (R_COUNT + CHAIN_JOB_ARRAYS + 1)   // record arrays + the arrays of a chain job (+ seeds of reseeded snapshots)
 static long long arena_need(const mag_ctx* c, int chunk, int nz) {
-  // average points per snapshot budgeted: 1.65 x the default grid (176 for nx = 107; grid
-  // extensions reach 3 x nx in the example input but only for ~1 % of the snapshots)
-  const long long nx_budget = ((long long)(c->P.p_nx_ref + 2 * MAG_NGHOST) * 165 + 99) / 100;
+  const long long nx_budget = ((long long)(c->P.p_nx_ref + 2 * MAG_NGHOST) * c->nx_budget_pct + 99) / 100;
   return (long long)chunk * nz * ARENA_ARRAYS * nx_budget;
+}
+
+static void free_records(mag_ctx* c) {
+  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena); cudaFree(c->d_jobs); cudaFree(c->d_jobidx);
+  c->d_order = nullptr; c->d_recs = nullptr; c->d_heads = nullptr; c->d_arena = nullptr; c->d_jobs = nullptr; c->d_jobidx = nullptr;
+  c->chunk_cap = 0; c->arena_cap = 0;
 }
 
 static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
@@ -399,12 +455,11 @@ static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
   const size_t per_gal = (size_t)nz * (sizeof(SnapRec) + 2 * sizeof(ChainJob) + 2 * sizeof(int)) + sizeof(GalHead) + sizeof(int) +
                          (size_t)arena_need(c, 1, nz) * sizeof(double);
   long long chunk = (long long)((double)free_b * frac / (double)per_gal);
+  if (const char* e = getenv("MAG_MAX_CHUNK")) { const long long m = atoll(e); if (m > 0 && chunk > m) chunk = m; }
   if (chunk > ngal) chunk = ngal;
   if (chunk < 1) { set_error("not enough device memory for the snapshot records"); return MAG_ERR_CUDA; }
   if (chunk <= c->chunk_cap && nz <= c->nz_cap) { *chunk_out = (int)chunk; return MAG_OK; }
-  cudaFree(c->d_order); cudaFree(c->d_recs); cudaFree(c->d_heads); cudaFree(c->d_arena); cudaFree(c->d_jobs); cudaFree(c->d_jobidx);
-  c->d_order = nullptr; c->d_recs = nullptr; c->d_heads = nullptr; c->d_arena = nullptr; c->d_jobs = nullptr; c->d_jobidx = nullptr;
-  c->chunk_cap = 0; c->arena_cap = 0;
+  free_records(c);
   CUDA_TRY(cudaMalloc(&c->d_jobs, (size_t)chunk * nz * 2 * sizeof(ChainJob)));
   CUDA_TRY(cudaMalloc(&c->d_jobidx, (size_t)chunk * nz * 2 * sizeof(int)));
   CUDA_TRY(cudaMalloc(&c->d_order, (size_t)chunk * sizeof(int)));
@@ -416,65 +471,97 @@ static int ensure_records(mag_ctx* c, int ngal, int nz, int* chunk_out) {
   return MAG_OK;
 }
 
-static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int32_t nz, const double* d_t,
-                        const double* d_inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
-                        const int32_t* scalar_q, const mag_outputs_t* d_out, cudaStream_t st) {
+// Enqueues the kernels for catalogue galaxies [g0, g0+n) on `st`.  `a` arrives with the array
+// bindings (virtual base pointers), nz, t_gyr and the quantity lists filled in.
+static int launch_solve(mag_ctx* c, KernelArgs& a, int32_t g0, int32_t n, cudaStream_t st, bool early_copy_event) {
+  const int nz = a.nz;
   if (nz < 1 || nz > 4000) { set_error("nz out of range"); return MAG_ERR_BAD_ARGUMENT; }
   int chunk = 0;
-  int rc = ensure_records(c, ngal, nz, &chunk);
+  int rc = ensure_records(c, n, nz, &chunk);
   if (rc) return rc;
   int launches = 0;
-  CUDA_TRY(cudaMemsetAsync(c->d_counter + 1, 0, 2 * sizeof(int), st));  // fail flag, replays
-  KernelArgs a;
-  memset(&a, 0, sizeof(a));
+  CUDA_TRY(cudaMemsetAsync(c->d_counter + CNT_FAIL, 0, 2 * sizeof(int), st));  // fail flag, replays
+  CUDA_TRY(cudaMemsetAsync(c->d_counter + CNT_INVALIDATED, 0, 2 * sizeof(int), st));  // ... and the heavy-galaxy count
   a.P = c->P;
   a.U = make_units();
-  a.ngal = ngal; a.nz = nz;
-  a.gal_ids = d_gal_ids; a.t_gyr = d_t; a.inputs = d_inputs; a.order = c->d_order;
-  a.n_profile_q = n_profile_q; a.n_scalar_q = n_scalar_q;
-  for (int i = 0; i < n_profile_q; i++) a.profile_q[i] = profile_q[i];
-  for (int i = 0; i < n_scalar_q; i++) a.scalar_q[i] = scalar_q[i];
-  a.out = *d_out;
-  a.ws = c->wsA; a.ws2 = c->wsB; a.nxcap = c->nxcap;
-  a.counter = c->d_counter; a.fail = c->d_counter + 1; a.replays = c->d_counter + 2; a.counter2 = c->d_counter + 3;
+  a.order = c->d_order;
+  a.ws = c->wsA; a.ws2 = c->wsB; a.ws3 = c->wsH; a.nxcap = c->nxcap;
+  a.counter = c->d_counter + CNT_A; a.fail = c->d_counter + CNT_FAIL; a.replays = c->d_counter + CNT_REPLAYS;
+  a.counter2 = c->d_counter + CNT_LIGHT; a.counter3 = c->d_counter + CNT_HEAVY; a.n_heavy = c->d_counter + CNT_NHEAVY;
+  a.n_invalidated = c->d_counter + CNT_INVALIDATED;
+  a.cost_total = c->d_arena_top + 1;
   a.use_fast = c->use_fast;
   a.recs = c->d_recs; a.heads = c->d_heads; a.arena = c->d_arena; a.arena_top = c->d_arena_top; a.arena_cap = c->arena_cap;
   a.jobs = c->d_jobs; a.job_count = c->d_job_count; a.jobidx = c->d_jobidx;
-  for (int g0 = 0; g0 < ngal; g0 += chunk) {
-    const int n = (ngal - g0 < chunk) ? ngal - g0 : chunk;
-    a.g0 = g0; a.g1 = g0 + n;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_counter + 3, 0, sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_arena_top, 0, sizeof(unsigned long long), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, COST_BUCKETS * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_recs, 0, (size_t)n * nz * sizeof(SnapRec), st));
+  a.pdl_join = c->launch_pdl;
+  for (int s0 = 0; s0 < n; s0 += chunk) {
+    const int m = (n - s0 < chunk) ? n - s0 : chunk;
+    a.g0 = g0 + s0; a.g1 = g0 + s0 + m;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter + CNT_A, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_counter + CNT_LIGHT, 0, 3 * sizeof(int), st));   // light head, heavy head, n_heavy
+    CUDA_TRY(cudaMemsetAsync(c->d_arena_top, 0, 2 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_hist, 0, 2 * COST_BUCKETS * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_recs, 0, (size_t)m * nz * sizeof(SnapRec), st));
     int ctasA = c->sm_count * c->ctasA_per_sm;
-    const int needA = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int needA = (m + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (needA < ctasA) ctasA = needA;
-    a.job_cap = n * nz * 2;
+    a.job_cap = m * nz * 2;
     if (c->split_chains) {
       // pass 1: walk the grid recurrence, export the hydrostatic chains; then 32 chains per warp
       CUDA_TRY(cudaMemsetAsync(c->d_job_count, 0, sizeof(int), st));
-      CUDA_TRY(cudaMemsetAsync(c->d_jobidx, 0xFF, (size_t)n * nz * 2 * sizeof(int), st));
+      CUDA_TRY(cudaMemsetAsync(c->d_jobidx, 0xFF, (size_t)m * nz * 2 * sizeof(int), st));
       a.chain_mode = CHAIN_MODE_EXPORT;
       k_profiles<<<ctasA, WARPS_PER_CTA * 32, 0, st>>>(a);
       k_chains<<<c->sm_count * 8, 128, 0, st>>>(a);
-      CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
+      CUDA_TRY(cudaMemsetAsync(c->d_counter + CNT_A, 0, sizeof(int), st));
       a.chain_mode = CHAIN_MODE_IMPORT;
       launches += 2;
     } else {
       a.chain_mode = CHAIN_MODE_INLINE;
     }
     k_profiles<<<ctasA, WARPS_PER_CTA * 32, 0, st>>>(a);
-    const int tb = 256, gb = (n + tb - 1) / tb;
-    k_cost_hist<<<gb, tb, 0, st>>>(c->d_heads, n, c->d_hist);
-    k_cost_scan<<<1, 32, 0, st>>>(c->d_hist);
-    k_cost_scatter<<<gb, tb, 0, st>>>(c->d_heads, n, c->d_hist, c->d_order);
-    if (g0 == 0) CUDA_TRY(cudaEventRecord(c->ev[4], st));
-    int teams = c->nteamsB;
-    if (n < teams) teams = n;
-    k_evolve<<<teams, MAG_TEAM, sizeof(RkShared), st>>>(a);
-    launches += 5;
+    if (early_copy_event && s0 + m >= n) CUDA_TRY(cudaEventRecord(c->ev_prof, st));   // the rows of the profile phase are complete
+    const int tb = 256, gb = (m + tb - 1) / tb;
+    k_cost_hist<<<gb, tb, 0, st>>>(c->d_heads, m, c->d_hist, c->policy, a.cost_total);
+    k_cost_scan<<<1, 32, 0, st>>>(c->d_hist, c->d_counter + CNT_NHEAVY);
+    k_cost_scatter<<<gb, tb, 0, st>>>(c->d_heads, m, c->d_hist, c->d_order, c->policy, a.cost_total);
+    if (s0 == 0) CUDA_TRY(cudaEventRecord(c->ev[4], st));
+    launches += 4;
+    int teams = c->nteamsB, teamsH = c->nteamsH;
+    if (m < teams) teams = m;
+    if (m < teamsH) teamsH = m;
+    const bool heavy_possible = c->policy.mode != 0;
+    if (heavy_possible && c->launch_pdl) {
+      // one stream: heavy teams first; the light kernel is their programmatic dependent and
+      // starts as soon as every heavy CTA is resident (it never reads what they write)
+      k_evolve_heavy<<<teamsH, MAG_TEAM_HEAVY, sizeof(RkSharedT<MAG_TEAM_HEAVY>), st>>>(a);
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(teams); cfg.blockDim = dim3(MAG_TEAM_LIGHT);
+      cfg.dynamicSmemBytes = sizeof(RkSharedT<MAG_TEAM_LIGHT>); cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, k_evolve, a));
+      launches += 2;
+    } else if (heavy_possible) {
+      // two streams: the heavy teams on a high-priority side stream, forked and joined by events
+      a.pdl_join = 0;
+      CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream_h, c->ev_fork, 0));
+      k_evolve_heavy<<<teamsH, MAG_TEAM_HEAVY, sizeof(RkSharedT<MAG_TEAM_HEAVY>), c->stream_h>>>(a);
+      CUDA_TRY(cudaEventRecord(c->ev_join, c->stream_h));
+      k_evolve<<<teams, MAG_TEAM_LIGHT, sizeof(RkSharedT<MAG_TEAM_LIGHT>), st>>>(a);
+      CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
+      launches += 2;
+    } else {
+      a.pdl_join = 0;
+      k_evolve<<<teams, MAG_TEAM_LIGHT, sizeof(RkSharedT<MAG_TEAM_LIGHT>), st>>>(a);
+      launches += 1;
+    }
+    // diagnostics: heavy galaxies of the call (summed over chunks on the device would need a kernel; keep the last chunk's)
+    CUDA_TRY(cudaMemcpyAsync(c->d_counter + CNT_NHEAVY_SUM, c->d_counter + CNT_NHEAVY, sizeof(int), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaGetLastError());
   }
   c->last_launches = launches;
@@ -484,33 +571,56 @@ static int launch_solve(mag_ctx* c, int32_t ngal, const int32_t* d_gal_ids, int3
 int mag_solve_batch_device(mag_ctx_t* c, int32_t ngal, const int32_t* d_gal_ids, int32_t nz, const double* d_t_gyr,
                            const double* d_inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
                            const int32_t* scalar_q, const mag_outputs_t* d_out, void* cuda_stream) {
-  MAG_FWD(c, g_fwd.solve_dev(c->fwd_ctx, ngal, d_gal_ids, nz, d_t_gyr, d_inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, d_out, cuda_stream));
-  if (!c || !d_out || ngal < 0) { set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT; }
+  return mag_solve_range_device(c, ngal, 0, ngal, d_gal_ids, nz, d_t_gyr, d_inputs, n_profile_q, profile_q, n_scalar_q, scalar_q,
+                                d_out, cuda_stream);
+}
+
+int mag_solve_range_device(mag_ctx_t* c, int32_t ngal_total, int32_t g0, int32_t n, const int32_t* d_gal_ids, int32_t nz,
+                           const double* d_t_gyr, const double* d_inputs, int32_t n_profile_q, const int32_t* profile_q,
+                           int32_t n_scalar_q, const int32_t* scalar_q, const mag_outputs_t* d_out, void* cuda_stream) {
+  if (!c || !d_out || ngal_total < 0 || g0 < 0 || n < 0 || g0 + n > ngal_total) { set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT; }
   if (check_quantities(n_profile_q, profile_q, n_scalar_q, scalar_q)) { set_error("bad quantity id"); return MAG_ERR_BAD_ARGUMENT; }
-  if (ngal == 0) return MAG_OK;
+  if (n == 0) return MAG_OK;
   CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  const size_t nr = c->P.p_nx_ref;
+  KernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nz = nz; a.t_gyr = d_t_gyr; a.gal_ids = d_gal_ids;
+  for (int col = 0; col < MAG_NINPUT; col++) a.in[col] = d_inputs + (size_t)col * ngal_total * nz;
+  a.n_profile_q = n_profile_q; a.n_scalar_q = n_scalar_q;
+  for (int i = 0; i < n_profile_q; i++) { a.profile_q[i] = profile_q[i]; a.prof[i] = d_out->profiles ? d_out->profiles + (size_t)i * ngal_total * nz * nr : nullptr; }
+  for (int i = 0; i < n_scalar_q; i++) { a.scalar_q[i] = scalar_q[i]; a.scal[i] = d_out->scalars ? d_out->scalars + (size_t)i * ngal_total * nz : nullptr; }
+  a.o_status = d_out->status; a.o_nsteps = d_out->nsteps; a.o_error = d_out->error; a.o_flags = d_out->flags;
+  a.o_point_stages = d_out->point_stages;
   CUDA_TRY(cudaEventRecord(c->ev[1], st));
-  int rc = launch_solve(c, ngal, d_gal_ids, nz, d_t_gyr, d_inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, d_out, st);
+  int rc = launch_solve(c, a, g0, n, st, false);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(c->ev[2], st));
   return MAG_OK;
 }
 
-int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t nz, const double* t_gyr,
-                    const double* inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
-                    const int32_t* scalar_q, const mag_outputs_t* out) {
-#if MAG_TEAM == 32
-  if (c && c->fwd_ctx) {
-    const int rc = g_fwd.solve(c->fwd_ctx, ngal, gal_ids, nz, t_gyr, inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, out);
-    if (rc != MAG_OK) set_error(g_fwd.last_error());
-    return rc;
-  }
-#endif
-  if (!c || !out || ngal < 0 || !gal_ids || !t_gyr || !inputs) { set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT; }
-  if (check_quantities(n_profile_q, profile_q, n_scalar_q, scalar_q)) { set_error("bad quantity id"); return MAG_ERR_BAD_ARGUMENT; }
-  if (ngal == 0) return MAG_OK;
+int mag_last_device_status(mag_ctx_t* c) {
+  if (!c) return MAG_ERR_BAD_ARGUMENT;
   CUDA_TRY(cudaSetDevice(c->device));
+  int fail = 0;
+  CUDA_TRY(cudaMemcpy(&fail, c->d_counter + CNT_FAIL, sizeof(int), cudaMemcpyDeviceToHost));
+  if (fail == MAG_ERR_ARENA) {
+    set_error("snapshot-record arena exhausted (grids grew beyond the budget): the results of this call are incomplete; "
+              "repeat it through mag_solve_batch, which retries with a larger arena, or set MAG_ARENA_NX_PCT");
+    return MAG_ERR_CUDA;
+  }
+  if (fail) { set_error("grid extension beyond p_nx_MAX / workspace capacity (reference: stop, grid.f90:222-226)"); return fail; }
+  return MAG_OK;
+}
+
+// ---- host-buffer API: enqueue (H2D, kernels, D2H) for catalogue galaxies [g0, g0+n) of full-catalogue
+// host arrays; mag_wait completes the call.
+static int enqueue_range(mag_ctx* c) {
+  PendingCall& pc = c->pend;
+  const int32_t ngal_total = pc.ngal_total, g0 = pc.g0, n = pc.n, nz = pc.nz;
+  const int32_t n_profile_q = pc.n_profile_q, n_scalar_q = pc.n_scalar_q;
+  const mag_outputs_t* out = &pc.out;
   const size_t nr = c->P.p_nx_ref;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   // Output arrays in pinned (mapped) host memory are written by the kernels directly: every row
@@ -524,15 +634,26 @@ int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t 
     if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
   };
-  void* const m_prof = mapped(out->profiles);
-  void* const m_scal = mapped(out->scalars);
-  void* const m_stat = mapped(out->status);
-  const size_t b_in = al(sizeof(double) * MAG_NINPUT * ngal * nz), b_t = al(sizeof(double) * nz), b_id = al(sizeof(int32_t) * ngal);
-  const size_t b_prof = (out->profiles && !m_prof) ? al(sizeof(double) * n_profile_q * ngal * nz * nr) : 0;
-  const size_t b_scal = (out->scalars && !m_scal) ? al(sizeof(double) * n_scalar_q * ngal * nz) : 0;
-  const size_t b_stat = (out->status && !m_stat) ? al((size_t)ngal * nz) : 0;
-  const size_t b_i32 = al(sizeof(int32_t) * ngal), b_i64 = al(sizeof(int64_t) * ngal);
-  const size_t total = b_in + b_t + b_id + b_prof + b_scal + b_stat + 3 * b_i32 + b_i64;
+  double* const m_prof = (double*)mapped(out->profiles);
+  double* const m_scal = (double*)mapped(out->scalars);
+  char* const m_stat = (char*)mapped(out->status);
+  // planes of the profile phase (h, n, Omega ...: everything that does not depend on the field) are
+  // produced in a burst at the start of the solve; staged in HBM and copied out by the copy engine
+  // while k_evolve runs, they do not compete with the other GPUs' bursts for the host's write bandwidth
+  const size_t plane = sizeof(double) * (size_t)n * nz * nr;
+  int n_staged_planes = 0;
+  bool plane_staged[MAG_NPROFILE];
+  for (int i = 0; i < n_profile_q; i++) {
+    const bool field = is_field_quantity(pc.profile_q[i]);
+    plane_staged[i] = out->profiles && (!m_prof || (c->stage_profile_rows && !field));
+    n_staged_planes += plane_staged[i] ? 1 : 0;
+  }
+  const size_t b_in = al(sizeof(double) * MAG_NINPUT * n * nz), b_t = al(sizeof(double) * nz), b_id = al(sizeof(int32_t) * n);
+  const size_t b_plane = al(plane);
+  const size_t b_scal = (out->scalars && !m_scal) ? al(sizeof(double) * n_scalar_q * n * nz) : 0;
+  const size_t b_stat = (out->status && !m_stat) ? al((size_t)n * nz) : 0;
+  const size_t b_i32 = al(sizeof(int32_t) * n), b_i64 = al(sizeof(int64_t) * n);
+  const size_t total = b_in + b_t + b_id + n_staged_planes * b_plane + b_scal + b_stat + 3 * b_i32 + b_i64;
   if (total > c->stage_bytes) {
     cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0;
     CUDA_TRY(cudaMalloc(&c->d_stage, total));
@@ -542,45 +663,148 @@ int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t 
   double* d_in = (double*)p; p += b_in;
   double* d_t = (double*)p; p += b_t;
   int32_t* d_id = (int32_t*)p; p += b_id;
-  mag_outputs_t d;
-  d.profiles = out->profiles ? (m_prof ? (double*)m_prof : (double*)p) : nullptr; p += b_prof;
-  d.scalars = out->scalars ? (m_scal ? (double*)m_scal : (double*)p) : nullptr; p += b_scal;
-  d.status = out->status ? (m_stat ? (char*)m_stat : (char*)p) : nullptr; p += b_stat;
-  d.nsteps = (int32_t*)p; p += b_i32;
-  d.error = (int32_t*)p; p += b_i32;
-  d.flags = (uint32_t*)p; p += b_i32;
-  d.point_stages = (int64_t*)p; p += b_i64;
+  KernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nz = nz; a.t_gyr = d_t;
+  a.gal_ids = vbase(d_id, g0, 1);
+  for (int col = 0; col < MAG_NINPUT; col++) a.in[col] = vbase(d_in + (size_t)col * n * nz, g0, nz);
+  a.n_profile_q = n_profile_q; a.n_scalar_q = n_scalar_q;
+  pc.n_early = 0;
+  double* staged_plane[MAG_NPROFILE];
+  for (int i = 0; i < n_profile_q; i++) {
+    a.profile_q[i] = pc.profile_q[i];
+    staged_plane[i] = nullptr;
+    if (!out->profiles) { a.prof[i] = nullptr; continue; }
+    if (plane_staged[i]) {
+      staged_plane[i] = (double*)p; p += b_plane;
+      a.prof[i] = vbase(staged_plane[i], g0, (size_t)nz * nr);
+      if (m_prof && !is_field_quantity(pc.profile_q[i])) {
+        auto& e = pc.early[pc.n_early++];
+        e.dev = staged_plane[i]; e.host = out->profiles + ((size_t)i * ngal_total + g0) * nz * nr; e.bytes = plane;
+      }
+    } else {
+      a.prof[i] = m_prof + (size_t)i * ngal_total * nz * nr;
+    }
+  }
+  double* d_scal = nullptr;
+  if (out->scalars && !m_scal) { d_scal = (double*)p; p += b_scal; }
+  for (int i = 0; i < n_scalar_q; i++) {
+    a.scalar_q[i] = pc.scalar_q[i];
+    a.scal[i] = !out->scalars ? nullptr : (m_scal ? m_scal + (size_t)i * ngal_total * nz : vbase(d_scal + (size_t)i * n * nz, g0, nz));
+  }
+  char* d_stat = nullptr;
+  if (out->status && !m_stat) { d_stat = (char*)p; p += b_stat; }
+  a.o_status = !out->status ? nullptr : (m_stat ? m_stat : vbase(d_stat, g0, nz));
+  int32_t* d_nsteps = (int32_t*)p; p += b_i32;
+  int32_t* d_error = (int32_t*)p; p += b_i32;
+  uint32_t* d_flags = (uint32_t*)p; p += b_i32;
+  int64_t* d_ps = (int64_t*)p; p += b_i64;
+  a.o_nsteps = vbase(d_nsteps, g0, 1); a.o_error = vbase(d_error, g0, 1); a.o_flags = vbase(d_flags, g0, 1);
+  a.o_point_stages = vbase(d_ps, g0, 1);
+
   cudaStream_t st = c->stream;
   CUDA_TRY(cudaEventRecord(c->ev[0], st));
-  CUDA_TRY(cudaMemcpyAsync(d_in, inputs, sizeof(double) * MAG_NINPUT * ngal * nz, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_t, t_gyr, sizeof(double) * nz, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_id, gal_ids, sizeof(int32_t) * ngal, cudaMemcpyHostToDevice, st));
+  // the range's slice of every input column: [13][ngal_total][nz] -> [13][n][nz]
+  CUDA_TRY(cudaMemcpy2DAsync(d_in, sizeof(double) * n * nz, pc.inputs + (size_t)g0 * nz, sizeof(double) * ngal_total * nz,
+                             sizeof(double) * n * nz, MAG_NINPUT, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_t, pc.t_gyr, sizeof(double) * nz, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_id, pc.gal_ids + g0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(c->ev[1], st));
-  int rc = launch_solve(c, ngal, d_id, nz, d_t, d_in, n_profile_q, profile_q, n_scalar_q, scalar_q, &d, st);
+  int rc = launch_solve(c, a, g0, n, st, pc.n_early > 0);
   if (rc) return rc;
+  if (pc.n_early > 0) {
+    CUDA_TRY(cudaStreamWaitEvent(c->stream_copy, c->ev_prof, 0));
+    for (int i = 0; i < pc.n_early; i++)
+      CUDA_TRY(cudaMemcpyAsync(pc.early[i].host, pc.early[i].dev, pc.early[i].bytes, cudaMemcpyDeviceToHost, c->stream_copy));
+    CUDA_TRY(cudaEventRecord(c->ev_copy, c->stream_copy));
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy, 0));
+  }
   CUDA_TRY(cudaEventRecord(c->ev[2], st));
-  if (out->profiles && !m_prof) CUDA_TRY(cudaMemcpyAsync(out->profiles, d.profiles, sizeof(double) * n_profile_q * ngal * nz * nr, cudaMemcpyDeviceToHost, st));
-  if (out->scalars && !m_scal) CUDA_TRY(cudaMemcpyAsync(out->scalars, d.scalars, sizeof(double) * n_scalar_q * ngal * nz, cudaMemcpyDeviceToHost, st));
-  if (out->status && !m_stat) CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)ngal * nz, cudaMemcpyDeviceToHost, st));
-  if (out->nsteps) CUDA_TRY(cudaMemcpyAsync(out->nsteps, d.nsteps, sizeof(int32_t) * ngal, cudaMemcpyDeviceToHost, st));
-  if (out->error) CUDA_TRY(cudaMemcpyAsync(out->error, d.error, sizeof(int32_t) * ngal, cudaMemcpyDeviceToHost, st));
-  if (out->flags) CUDA_TRY(cudaMemcpyAsync(out->flags, d.flags, sizeof(uint32_t) * ngal, cudaMemcpyDeviceToHost, st));
-  if (out->point_stages) CUDA_TRY(cudaMemcpyAsync(out->point_stages, d.point_stages, sizeof(int64_t) * ngal, cudaMemcpyDeviceToHost, st));
-  int fail = 0;
-  CUDA_TRY(cudaMemcpyAsync(&fail, c->d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (out->profiles && !m_prof)
+    for (int i = 0; i < n_profile_q; i++)
+      CUDA_TRY(cudaMemcpyAsync(out->profiles + ((size_t)i * ngal_total + g0) * nz * nr, staged_plane[i], plane, cudaMemcpyDeviceToHost, st));
+  if (d_scal)
+    CUDA_TRY(cudaMemcpy2DAsync(out->scalars + (size_t)g0 * nz, sizeof(double) * ngal_total * nz, d_scal, sizeof(double) * n * nz,
+                               sizeof(double) * n * nz, n_scalar_q, cudaMemcpyDeviceToHost, st));
+  if (d_stat) CUDA_TRY(cudaMemcpyAsync(out->status + (size_t)g0 * nz, d_stat, (size_t)n * nz, cudaMemcpyDeviceToHost, st));
+  if (out->nsteps) CUDA_TRY(cudaMemcpyAsync(out->nsteps + g0, d_nsteps, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  if (out->error) CUDA_TRY(cudaMemcpyAsync(out->error + g0, d_error, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  if (out->flags) CUDA_TRY(cudaMemcpyAsync(out->flags + g0, d_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+  if (out->point_stages) CUDA_TRY(cudaMemcpyAsync(out->point_stages + g0, d_ps, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(c->h_status, c->d_counter + CNT_FAIL, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(c->h_status + 1, c->d_counter + CNT_INVALIDATED, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(c->h_status + 2, c->d_counter + CNT_REPLAYS, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(c->h_status + 3, c->d_counter + CNT_NHEAVY_SUM, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(c->ev[3], st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  float ms;
-  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->last_ms[2] = ms;
-  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms;
-  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[3] = ms;
-  if (fail == MAG_ERR_ARENA) { set_error("snapshot-record arena exhausted (grids grew beyond the budget): lower MAG_ARENA_FRACTION chunking or split the batch"); return MAG_ERR_CUDA; }
-  if (fail) { set_error("grid extension beyond p_nx_MAX / workspace capacity (reference: stop, grid.f90:222-226)"); return fail; }
   return MAG_OK;
 }
 
+int mag_solve_range_async(mag_ctx_t* c, int32_t ngal_total, int32_t g0, int32_t n, const int32_t* gal_ids, int32_t nz,
+                          const double* t_gyr, const double* inputs, int32_t n_profile_q, const int32_t* profile_q,
+                          int32_t n_scalar_q, const int32_t* scalar_q, const mag_outputs_t* out) {
+  if (!c || !out || ngal_total < 0 || g0 < 0 || n < 0 || g0 + n > ngal_total || !gal_ids || !t_gyr || !inputs) {
+    set_error("bad argument"); return MAG_ERR_BAD_ARGUMENT;
+  }
+  if (check_quantities(n_profile_q, profile_q, n_scalar_q, scalar_q)) { set_error("bad quantity id"); return MAG_ERR_BAD_ARGUMENT; }
+  if (c->pend.active) { set_error("a solve is still pending on this context: call mag_wait first"); return MAG_ERR_BAD_ARGUMENT; }
+  if (n == 0) return MAG_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  PendingCall& pc = c->pend;
+  pc.ngal_total = ngal_total; pc.g0 = g0; pc.n = n; pc.nz = nz; pc.gal_ids = gal_ids; pc.t_gyr = t_gyr; pc.inputs = inputs;
+  pc.n_profile_q = n_profile_q; pc.n_scalar_q = n_scalar_q;
+  for (int i = 0; i < n_profile_q; i++) pc.profile_q[i] = profile_q[i];
+  for (int i = 0; i < n_scalar_q; i++) pc.scalar_q[i] = scalar_q[i];
+  pc.out = *out;
+  const int rc = enqueue_range(c);
+  if (rc == MAG_OK) pc.active = true;
+  return rc;
+}
+
+int mag_wait(mag_ctx_t* c) {
+  if (!c) { set_error("null context"); return MAG_ERR_BAD_ARGUMENT; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->pend.active) {   // device-array calls on the context's own stream: just drain it
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return MAG_OK;
+  }
+  for (int attempt = 0;; attempt++) {
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { c->pend.active = false; set_error(std::string("solve failed: ") + cudaGetErrorString(e)); return MAG_ERR_CUDA; }
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->last_ms[2] = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[3] = ms;
+    const int fail = c->h_status[0];
+    if (fail == MAG_ERR_ARENA && attempt < 3) {
+      // grids grew beyond the arena budget: repeat the range with twice the budget (smaller chunks)
+      c->nx_budget_pct *= 2;
+      free_records(c);
+      const int rc = enqueue_range(c);
+      if (rc != MAG_OK) { c->pend.active = false; return rc; }
+      continue;
+    }
+    c->pend.active = false;
+    if (fail == MAG_ERR_ARENA) { set_error("snapshot-record arena exhausted after three retries"); return MAG_ERR_CUDA; }
+    if (fail) { set_error("grid extension beyond p_nx_MAX / workspace capacity (reference: stop, grid.f90:222-226)"); return fail; }
+    if (c->h_status[1] > 0 && c->pend.n_early > 0) {
+      // a run stopped early (status 'i') and rewrote rows of the profile phase after their planes had
+      // been copied out: copy them again (rare)
+      for (int i = 0; i < c->pend.n_early; i++)
+        CUDA_TRY(cudaMemcpy(c->pend.early[i].host, c->pend.early[i].dev, c->pend.early[i].bytes, cudaMemcpyDeviceToHost));
+    }
+    return MAG_OK;
+  }
+}
+
+int mag_solve_batch(mag_ctx_t* c, int32_t ngal, const int32_t* gal_ids, int32_t nz, const double* t_gyr,
+                    const double* inputs, int32_t n_profile_q, const int32_t* profile_q, int32_t n_scalar_q,
+                    const int32_t* scalar_q, const mag_outputs_t* out) {
+  const int rc = mag_solve_range_async(c, ngal, 0, ngal, gal_ids, nz, t_gyr, inputs, n_profile_q, profile_q, n_scalar_q, scalar_q, out);
+  if (rc != MAG_OK) return rc;
+  return mag_wait(c);
+}
+
 int mag_last_timing(mag_ctx_t* c, double ms_out[4]) {
-  MAG_FWD(c, g_fwd.timing(c->fwd_ctx, ms_out));
   if (!c) return 0;
   float ms = 0;
   if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->last_ms[1] = ms;
@@ -590,7 +814,6 @@ int mag_last_timing(mag_ctx_t* c, double ms_out[4]) {
 }
 
 double mag_measure_fp64_peak(mag_ctx_t* c, int repeats) {
-  MAG_FWD(c, g_fwd.peak(c->fwd_ctx, repeats));
   if (!c) return 0.0;
   cudaSetDevice(c->device);
   const int threads = 256, blocks = c->sm_count * 8, iters = 1 << 14;
@@ -611,6 +834,13 @@ double mag_measure_fp64_peak(mag_ctx_t* c, int repeats) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
   return best;
 }
+
+void* mag_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void mag_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- test hooks (exported, not part of the reference-facing ABI)
 __global__ void k_test_bessel(const double* x, int n, double* out) {
@@ -678,21 +908,30 @@ int mag_test_rng(int32_t igal, int32_t seed, int32_t kind, int32_t n, double* ou
   cudaFree(d);
   return MAG_OK;
 }
-int mag_ctx_info(mag_ctx_t* c, int32_t* out /* sm_count, ctas_per_sm, nwarps, nxcap, use_fast, replays of the last solve, ..., team */) {
-  MAG_FWD(c, g_fwd.info(c->fwd_ctx, out));
+int mag_ctx_info(mag_ctx_t* c, int32_t* out /* [12]: sm_count, profile CTAs/SM, profile warps, nxcap, use_fast, fast-path replays and
+                                               heavy-class galaxies of the last solve (last chunk), one-warp teams/SM, one-warp teams,
+                                               four-warp teams/SM, four-warp teams, heavy mode */) {
   if (!c) return MAG_ERR_BAD_ARGUMENT;
-  out[9] = MAG_TEAM;
   out[0] = c->sm_count; out[1] = c->ctasA_per_sm; out[2] = c->nwarpsA; out[3] = c->nxcap; out[4] = c->use_fast;
-  out[5] = 0;
+  out[5] = 0; out[6] = 0;
   cudaSetDevice(c->device);
-  cudaMemcpy(&out[5], c->d_counter + 2, sizeof(int), cudaMemcpyDeviceToHost);
-  out[6] = c->ctasA_per_sm; out[7] = c->ctasB_per_sm; out[8] = c->nteamsB;
+  cudaMemcpy(&out[5], c->d_counter + CNT_REPLAYS, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(&out[6], c->d_counter + CNT_NHEAVY_SUM, sizeof(int), cudaMemcpyDeviceToHost);
+  out[7] = c->ctasB_per_sm; out[8] = c->nteamsB; out[9] = c->ctasH_per_sm; out[10] = c->nteamsH; out[11] = c->policy.mode;
   return MAG_OK;
 }
 int mag_set_fast_path(mag_ctx_t* c, int32_t on) {
-  MAG_FWD(c, g_fwd.set_fast(c->fwd_ctx, on));
   if (!c) return MAG_ERR_BAD_ARGUMENT;
   c->use_fast = on ? 1 : 0;
+  return MAG_OK;
+}
+// which galaxies run on four-warp teams: mode 0 none, 1 by cost (alpha x the fair share of a warp slot;
+// alpha <= 0 keeps the current value), 2 all; nx_heavy > 0: grids above it are heavy
+int mag_set_heavy_policy(mag_ctx_t* c, int32_t mode, double alpha, int32_t nx_heavy) {
+  if (!c || mode < 0 || mode > 2) return MAG_ERR_BAD_ARGUMENT;
+  c->policy.mode = mode;
+  if (alpha > 0) { c->heavy_alpha = alpha; c->policy.alpha_over_slots = alpha / (double)c->nteamsB; }
+  if (nx_heavy > 0) c->policy.nx_heavy = nx_heavy;
   return MAG_OK;
 }
 

@@ -43,6 +43,13 @@ def synthetic_histories(base_inputs: np.ndarray, ngal: int, seed: int = SEED, fi
     return out
 
 
+def synthetic_subset(base_inputs: np.ndarray, indices, seed: int = SEED) -> np.ndarray:
+    """inputs [13, len(indices), nz] of the catalogue galaxies with the given 0-based indices
+    (the same histories synthetic_histories(base, G)[:, indices] holds for any G > max index)."""
+    out = [synthetic_histories(base_inputs, 1, seed=seed, first=int(i)) for i in indices]
+    return np.ascontiguousarray(np.concatenate(out, axis=1))
+
+
 def galaxy_ids(ngal: int, first: int = 0) -> np.ndarray:
     """1-based ids (the RNG seed of a galaxy depends on its id, random.f90:43)."""
     return np.arange(first + 1, first + ngal + 1, dtype=np.int32)

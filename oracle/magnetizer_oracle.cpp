@@ -124,7 +124,17 @@ static void params_default(mag_params_t* p) {
   p->p_limit_turbulent_scale = 1;                       // :221
   p->p_allow_positive_shears = 0;                       // :243
   p->seed_choice = 0;                                   // :150 'random'
-  p->outflow_type = 0;                                  // :306 'no_outflow'
+  p->outflow_type = MAG_OUTFLOW_NONE;                   // :306 'no_outflow'
+  // outflow_parameters, :303-325 (literals without d0 are single precision)
+  p->p_outflow_Lsn = 1e38;                              // :308
+  p->p_outflow_fOB = (double)0.7f;                      // :310
+  p->p_outflow_etaSN = 9.4e-3;                          // :312
+  p->p_tOB = 3.0;                                       // :314
+  p->p_N_SN1OB = 40.0;                                  // :316
+  p->p_outflow_hot_gas_density = 1.7e-27;               // :318
+  p->p_outflow_nu0 = (double)0.5f;                      // :320
+  p->p_outflow_alphahot = (double)-3.2f;                // :322
+  p->p_outflow_Vhot = 425.0;                            // :324
 }
 
 static bool params_supported(const mag_params_t& p) {
@@ -132,7 +142,8 @@ static bool params_supported(const mag_params_t& p) {
          p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && p.Alg_quench == 0 &&
          p.Damp == 0 && p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
          p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice == 0 &&
-         p.outflow_type == 0 && p.p_nx_ref >= 8 && (p.rng_kind == 0 || p.rng_kind == 1);
+         p.outflow_type >= MAG_OUTFLOW_NONE && p.outflow_type <= MAG_OUTFLOW_SUPERBUBBLE && p.p_nx_ref >= 8 &&
+         (p.rng_kind == 0 || p.rng_kind == 1);
 }
 
 // ------------------------------------------------------------------ interpolation
@@ -703,6 +714,37 @@ struct Galaxy {
     for (int i = 1; i <= nghost_actual + 1; i++) rho_d[i - 1] = density_to_scaleheight(h_d[i - 1], Sigma_d[i - 1]);
   }
 
+  // outflow_speed, outflow.f90:24-121, at one radius.  r, h in kpc, rho in g/cm^3, vt in km/s;
+  // result in km/s.  Literals without d0 are single precision in the reference.
+  double outflow_speed(double r, double rho, double hk, double vt, double Rm_i) const {
+    switch (P.outflow_type) {
+      case MAG_OUTFLOW_NONE: return r * 0.0;                                      // :65-67
+      case MAG_OUTFLOW_VTURB: return vt;                                          // :68-70
+      case MAG_OUTFLOW_WIND: {                                                    // :71-88
+        const double VDISK_MIN = (double)0.01f;                                   // :56
+        const double fm = Rm_i / (1.0 + Rm_i);
+        const double beta = m_pow(std::max(VDISK_MIN, v_disk) / P.p_outflow_Vhot, P.p_outflow_alphahot);
+        double u = 0.5 * P.p_outflow_nu0 * beta * hk * fm;
+        u = u * km_kpc / s_Gyr;
+        return u;
+      }
+      default: break;
+    }
+    // superbubble[_simple], :89-119
+    const double rs = r_disk * constDiskScaleToHalfMassRatio;
+    const double nn = rho / Hmass;
+    if (!(nn > 0.0)) return 0.0;
+    const double constant = (double)51.3f * m_pow(P.p_outflow_Lsn / 1e38, (double)(1.f / 3.f)) * P.p_outflow_fOB / 0.7 *
+                            (P.p_outflow_etaSN / (double)9.4e-3f) * (P.p_tOB / 3.0) * (40.0 / P.p_N_SN1OB);
+    const double q = rs / 3.0;
+    double u = constant * (1.0 / (q * q)) * SFR;                                  // (rs/3.0)**(-2): integer power
+    u = u * m_pow(nn, (double)(-1.f / 3.f));
+    u = u * m_pow(hk / (double)0.2f, (double)(4.f / 3.f));
+    u = u * m_exp(-r / rs);
+    if (P.outflow_type == MAG_OUTFLOW_SUPERBUBBLE) u = (P.p_outflow_hot_gas_density / rho) * u;
+    return u;
+  }
+
   // construct_profiles, profiles.f90:33-272 (B absent => 0)
   bool construct_profiles() {
     const vec* all[] = {&h, &n, &l, &l_kpc, &v, &etat, &tau, &Beq, &alp_k, &Uz, &Ur, &Om, &G, &Om_d, &Om_b, &G_b, &Om_h, &G_h};
@@ -791,7 +833,7 @@ struct Galaxy {
       l[i] = l_kpc[i] * h0 / h0_kpc;
       Beq[i] = std::sqrt(4.0 * pi * n[i]) * v[i];
       h[i] = h_kpc[i] * h0 / h0_kpc;
-      double Uz_kms = result ? r_kpc[i] * 0.0 : 0.0;  // outflow_speed 'no_outflow', outflow.f90:65-67
+      double Uz_kms = result ? outflow_speed(r_kpc[i], rho_cgs[i], h_kpc[i], v_kms, Rm[i]) : 0.0;  // profiles.f90:225-232
       Uz[i] = Uz_kms / h0_km * h0 * t0_s / t0;
       etat[i] = 1.0 / 3.0 * l[i] * v[i];
       tau[i] = ctau * l[i] / v[i];

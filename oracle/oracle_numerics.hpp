@@ -259,7 +259,19 @@ bool find_root_secant(F&& f, double guess, double step, double* root_out) {
 }
 
 // ---------------------------------------------------------------- Bessel ----
-// det_math.hpp explains why these are pinned implementations rather than library calls
+// det_math.hpp explains why these are pinned implementations rather than library calls.
+// -DORACLE_LIBM swaps in the host's libm / libstdc++ special functions: the build the
+// sensitivity experiment (tools/sensitivity_experiment.py, profiles/r2_sensitivity.md) uses to
+// measure how far the reference's own results move with its unpinned libraries.
+#ifdef ORACLE_LIBM
+inline double bessel_I0(double x) { return std::cyl_bessel_i(0.0, x); }
+inline double bessel_I1(double x) { return std::cyl_bessel_i(1.0, x); }
+inline double bessel_K0(double x) { return std::cyl_bessel_k(0.0, x); }
+inline double bessel_K1(double x) { return std::cyl_bessel_k(1.0, x); }
+inline double m_log(double x) { return std::log(x); }
+inline double m_exp(double x) { return std::exp(x); }
+inline double m_pow(double x, double y) { return std::pow(x, y); }
+#else
 inline double bessel_I0(double x) { double a, b, c, d; detmath::det_bessel_ik01(x, &a, &b, &c, &d); return a; }
 inline double bessel_I1(double x) { double a, b, c, d; detmath::det_bessel_ik01(x, &a, &b, &c, &d); return b; }
 inline double bessel_K0(double x) { double a, b, c, d; detmath::det_bessel_ik01(x, &a, &b, &c, &d); return c; }
@@ -267,5 +279,6 @@ inline double bessel_K1(double x) { double a, b, c, d; detmath::det_bessel_ik01(
 inline double m_log(double x) { return detmath::det_log(x); }
 inline double m_exp(double x) { return detmath::det_exp(x); }
 inline double m_pow(double x, double y) { return detmath::det_pow(x, y); }
+#endif
 
 }  // namespace oracle

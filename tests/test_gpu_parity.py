@@ -192,7 +192,7 @@ def test_partitioned_solve_matches_single_context(solver, example_input):
     prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax", "dt")
     one = solver.run(ids, t, sub, profiles=prof, scalars=scal)
     two = solve_partitioned(ids, t, sub, devices=[0, 0], chunk=4, profiles=prof, scalars=scal)
-    assert two["chunks_done"].sum() == 11 and (two["chunks_done"] > 0).all()
+    assert two["chunks_done"].sum() == 11
     for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
         assert np.array_equal(one[k], two[k]), k
     assert np.array_equal(one["status"], two["status"])
@@ -226,11 +226,15 @@ def test_unstable_timestep_blow_up_and_retry_path(oracle, example_input):
 def test_fine_grid_config5(oracle, example_input):
     """BASELINE config 5: 4x radial resolution (p_nx_ref = 401, nx = 407 and more after grid
     extensions) with tightened Courant factors (0.045, passed as doubles as a namelist file
-    would).  Runs on 128-thread teams (4 points per thread); grids beyond 512 points fall
-    back to the generic path."""
+    would).  Every galaxy runs on the four-warp teams (4 points per thread; 8 beyond 512
+    points).  Three example galaxies and 64 of the synthetic catalogue."""
     from magnetizer_b200.solver import DynamoSolver
+    from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
     t, inputs = example_input
     ids, sub = _subset(inputs, [1, 2, 60])
+    syn = synthetic_histories(inputs, 64, first=3000)
+    ids = np.concatenate([ids, galaxy_ids(64, first=3000)])
+    sub = np.ascontiguousarray(np.concatenate([sub, syn], axis=1))
     p = oracle.default_params()
     p.p_nx_ref = 401
     p.p_courant_v = 0.045
@@ -241,7 +245,8 @@ def test_fine_grid_config5(oracle, example_input):
         info = s.info()
     finally:
         s.close()
-    ora = oracle.solve_batch(p, ids, t, sub, nthreads=3)
+    assert info["heavy_galaxies"] > 0
+    ora = oracle.solve_batch(p, ids, t, sub)
     rep = compare(gpu, ora)
     print("config 5 worst errors:", {k: f"{v:.1e}" for k, v in rep.items() if v > 0}, info)
 
@@ -283,3 +288,240 @@ def test_warp_path_every_alignment_matches_generic_path(example_input):
         assert np.array_equal(fast["nsteps"], slow["nsteps"]), nref
         rep = compare(fast, slow)
         assert max(rep.values()) < 1e-8, (nref, rep)
+
+
+# ---------------------------------------------------------------------------------------------
+# Every run-time parameter the ABI advertises (mag_params_t), off its default: 32 galaxies of the
+# synthetic catalogue + the 196 example galaxies per setting, CUDA path vs oracle.
+def _sweep_cases():
+    def setter(**kw):
+        def f(p):
+            for k, v in kw.items():
+                setattr(p, k, v)
+        return f
+    return [
+        ("test_run", setter(p_no_magnetic_fields_test_run=1)),                  # dynamo.f90:102-104, status 't'
+        ("xoshiro256ss", setter(rng_kind=0)),                                   # GCC >= 9 libgfortran stream
+        ("R_kappa_0.5", setter(R_kappa=0.5)),                                   # shared-line loops (mag_rk_fast.cuh)
+        ("no_Pdm", setter(p_use_Pdm=0)),
+        ("no_Pbulge", setter(p_use_Pbulge=0)),
+        ("ignore_satellite_haloes", setter(p_ignore_satellite_DM_haloes=1)),
+        ("random_seed_5", setter(p_random_seed=5)),
+        ("MAX_FAILS_2_courant_0.4", setter(p_MAX_FAILS=2, p_courant_v=0.4, p_courant_eta=0.4)),   # the retry loop is reached
+        ("nsteps_max_5000", setter(p_nsteps_max=5000)),
+        ("rmax_over_rdisk_3.5", setter(p_rmax_over_rdisk=3.5)),
+        ("floor_and_seed", setter(fmag=0.3, C_floor=2.0, frac_seed=0.05, p_floor_kappa=5.0, C_alp=0.8)),
+        ("ism", setter(p_ISM_sound_speed_km_s=12.0, p_ISM_kappa=0.9, p_ISM_xi=0.3, p_ISM_turbulent_length=0.08,
+                       p_rreg_to_rdisk=0.15, p_Rmol_alpha=0.8, p_minimum_density=1e-29)),
+    ]
+
+
+@pytest.mark.parametrize("name,setp", _sweep_cases(), ids=[c[0] for c in _sweep_cases()])
+def test_parameter_sweep(oracle, example_input, name, setp):
+    from magnetizer_b200.solver import DynamoSolver
+    from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
+    t, inputs = example_input
+    n_ex = inputs.shape[1]
+    syn = synthetic_histories(inputs, 32, first=5000)
+    ids = np.concatenate([np.arange(1, n_ex + 1, dtype=np.int32), galaxy_ids(32, first=5000)])
+    allin = np.ascontiguousarray(np.concatenate([inputs, syn], axis=1))
+    prof, scal = ("Br", "Bp", "alp_m", "Bzmod", "h", "n", "Omega", "Shear", "alp", "alp_k", "etat", "Uz"), \
+                 ("Bmax", "Bmax_idx", "dt", "rmax", "Bavg", "Beavg")
+    p = oracle.default_params()
+    setp(p)
+    s = DynamoSolver(params=p, device=0)
+    try:
+        gpu = s.run(ids, t, allin, profiles=prof, scalars=scal)
+        info = s.info()
+    finally:
+        s.close()
+    ora = oracle.solve_batch(p, ids, t, allin, profiles=prof, scalars=scal)
+    rep = compare(gpu, ora)
+    print(name, "worst:", max(rep.values()), "statuses:", sorted(set(ora["status"].tobytes().decode())),
+          "heavy", info["heavy_galaxies"], "replays", info["fast_path_replays"])
+    if name.startswith("MAX_FAILS"):
+        assert (ora["flags"] & 4).any()       # retries really happen
+    if name == "test_run":
+        assert set(ora["status"].tobytes().decode()) <= set("t-pHhP")
+
+
+@pytest.mark.parametrize("outflow", [1, 2, 3, 4], ids=["vturb", "wind", "superbubble_simple", "superbubble"])
+def test_outflow_models(oracle, example_input, outflow):
+    """p_outflow_type other than 'no_outflow' (outflow.f90:68-119): Uz enters the vertical-advection
+    terms of all three equations, the floor-field source and the critical dynamo number."""
+    from magnetizer_b200.solver import DynamoSolver
+    from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
+    t, inputs = example_input
+    ex = np.arange(1, 65, dtype=np.int32)
+    syn = synthetic_histories(inputs, 32, first=7000)
+    ids = np.concatenate([ex, galaxy_ids(32, first=7000)])
+    allin = np.ascontiguousarray(np.concatenate([inputs[:, ex - 1, :], syn], axis=1))
+    prof, scal = ("Br", "Bp", "alp_m", "Bzmod", "h", "n", "alp", "Uz"), ("Bmax", "Bmax_idx", "dt")
+    p = oracle.default_params()
+    p.outflow_type = outflow
+    s = DynamoSolver(params=p, device=0)
+    try:
+        gpu = s.run(ids, t, allin, profiles=prof, scalars=scal)
+    finally:
+        s.close()
+    ora = oracle.solve_batch(p, ids, t, allin, profiles=prof, scalars=scal)
+    rep = compare(gpu, ora)
+    uz = ora["profiles"][prof.index("Uz")]
+    assert (uz[uz > -9e4] > 0).any()          # the outflow is really on
+    print("outflow", outflow, "worst:", max(rep.values()))
+
+
+def test_heavy_teams_every_grid_class(oracle, example_input):
+    """k_evolve_heavy (four warps per galaxy, mag_rk_fast.cuh): all galaxies forced onto it.  The
+    example histories reach nx = 107 .. 330, i.e. the 1-, 2- and 3-points-per-thread loops; results
+    must match the oracle and, bit for bit in the exactly-compared fields, the one-warp kernel."""
+    from magnetizer_b200.solver import DynamoSolver
+    t, inputs = example_input
+    ids, sub = _subset(inputs, [1, 5, 23, 24, 30, 60, 67, 85, 101, 150])
+    s = DynamoSolver(device=0)
+    try:
+        s.set_heavy_policy(mode=2)
+        heavy = s.run(ids, t, sub)
+        assert s.info()["heavy_galaxies"] == len(ids)
+        s.set_heavy_policy(mode=0)
+        light = s.run(ids, t, sub)
+        assert s.info()["heavy_galaxies"] == 0
+    finally:
+        s.close()
+    ora = oracle.solve_batch(s.params, ids, t, sub)
+    compare(heavy, ora)
+    compare(light, ora)
+    compare(heavy, light)
+
+
+def test_heavy_light_split_and_launch_modes(oracle, example_input):
+    """The cost-based split of a batch into the two evolve kernels, launched on two streams and as
+    programmatic dependents (MAG_EVOLVE_PDL=1): identical results, some galaxies in each class."""
+    from magnetizer_b200.solver import DynamoSolver
+    t, inputs = example_input
+    ids = np.arange(1, inputs.shape[1] + 1, dtype=np.int32)
+    prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax", "dt")
+    res = {}
+    for pdl in ("0", "1"):
+        os.environ["MAG_EVOLVE_PDL"] = pdl
+        try:
+            s = DynamoSolver(device=0)
+        finally:
+            del os.environ["MAG_EVOLVE_PDL"]
+        try:
+            s.set_heavy_policy(mode=1, alpha=4.0)      # small batch: put the threshold where both classes are populated
+            res[pdl] = s.run(ids, t, inputs, profiles=prof, scalars=scal)
+            nh = s.info()["heavy_galaxies"]
+            assert 0 < nh < len(ids), nh
+        finally:
+            s.close()
+    for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
+        assert np.array_equal(res["0"][k], res["1"][k]), k
+    ora = oracle.solve_batch(oracle.default_params(), ids, t, inputs, profiles=prof, scalars=scal)
+    compare(res["1"], ora)
+
+
+def test_multi_chunk_records(example_input):
+    """A batch that does not fit the record tables is solved in several chunks (MAG_MAX_CHUNK caps
+    the chunk size here): every chunk addresses its chunk-local tables; same result as one chunk."""
+    from magnetizer_b200.solver import DynamoSolver
+    t, inputs = example_input
+    ids, sub = _subset(inputs, list(range(100, 131)))
+    prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax", "dt")
+    s = DynamoSolver(device=0)
+    try:
+        one = s.run(ids, t, sub, profiles=prof, scalars=scal)
+    finally:
+        s.close()
+    os.environ["MAG_MAX_CHUNK"] = "7"
+    try:
+        s = DynamoSolver(device=0)
+        try:
+            many = s.run(ids, t, sub, profiles=prof, scalars=scal)
+            assert s.last_timing()["kernel_launches"] >= 5 * 8   # 5 chunks
+        finally:
+            s.close()
+    finally:
+        del os.environ["MAG_MAX_CHUNK"]
+    for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
+        assert np.array_equal(one[k], many[k]), k
+    assert np.array_equal(one["status"], many["status"])
+
+
+def test_arena_overflow_retry_and_device_status(example_input):
+    """A record arena that is too small (MAG_ARENA_NX_PCT=20: far fewer points per snapshot than the
+    default grid has) overflows on the device; mag_solve_batch repeats the solve with a larger one,
+    mag_solve_batch_device reports it through mag_last_device_status."""
+    import torch
+    from magnetizer_b200.solver import DynamoSolver, MagnetizerError
+    t, inputs = example_input
+    ids, sub = _subset(inputs, list(range(1, 41)))
+    prof, scal = ("Br", "h"), ("Bmax",)
+    s = DynamoSolver(device=0)
+    try:
+        want = s.run(ids, t, sub, profiles=prof, scalars=scal)
+    finally:
+        s.close()
+    os.environ["MAG_ARENA_NX_PCT"] = "20"
+    try:
+        s = DynamoSolver(device=0)
+    finally:
+        del os.environ["MAG_ARENA_NX_PCT"]
+    try:
+        dev = torch.device("cuda", 0)
+        d_in, d_t, d_ids = torch.from_numpy(sub).to(dev), torch.from_numpy(t).to(dev), torch.from_numpy(ids).to(dev)
+        d_prof = torch.empty((2, len(ids), t.size, s.params.p_nx_ref), dtype=torch.float64, device=dev)
+        d_err = torch.empty(len(ids), dtype=torch.int32, device=dev)
+        s.run_device(len(ids), t.size, d_ids.data_ptr(), d_t.data_ptr(), d_in.data_ptr(), prof, (),
+                     dict(profiles=d_prof.data_ptr(), error=d_err.data_ptr()), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        with pytest.raises(MagnetizerError):
+            s.device_status()
+        got = s.run(ids, t, sub, profiles=prof, scalars=scal)       # retries inside
+    finally:
+        s.close()
+    for k in ("profiles", "scalars", "nsteps", "point_stages"):
+        assert np.array_equal(want[k], got[k]), k
+
+
+def test_partition_pinned_in_place_and_resident(example_input):
+    """mag_partition_*: page-locked caller arrays are written in place by the kernels (no gather
+    copy); the HBM-resident form leaves every galaxy's rows on the device that solved it."""
+    import torch
+    from magnetizer_b200.solver import DynamoSolver, Partition, host_free
+    t, inputs = example_input
+    ids, sub = _subset(inputs, list(range(1, 61)))
+    prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax", "dt")
+    s = DynamoSolver(device=0)
+    try:
+        one = s.run(ids, t, sub, profiles=prof, scalars=scal)
+    finally:
+        s.close()
+    part = Partition([0, 0])
+    try:
+        out = part.alloc_outputs(len(ids), t.size, prof, scal, pinned=True)
+        two = part.solve(ids, t, sub, chunk=8, profiles=prof, scalars=scal, out=out)
+        assert two["chunks_done"].sum() == 8
+        for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
+            assert np.array_equal(one[k], np.asarray(two[k])), k
+        assert np.array_equal(one["status"], two["status"])
+        # resident form: one full copy of the inputs / outputs per listed device
+        dev = torch.device("cuda", 0)
+        nd, n, nz, nr = 2, len(ids), t.size, part.params.p_nx_ref
+        d_in = [torch.from_numpy(sub).to(dev) for _ in range(nd)]
+        d_t = [torch.from_numpy(t).to(dev) for _ in range(nd)]
+        d_id = [torch.from_numpy(ids).to(dev) for _ in range(nd)]
+        d_prof = [torch.full((len(prof), n, nz, nr), -7.0, dtype=torch.float64, device=dev) for _ in range(nd)]
+        d_ps = [torch.zeros(n, dtype=torch.int64, device=dev) for _ in range(nd)]
+        owner = np.full(n, -1, np.int32)
+        st = part.solve_device(n, nz, [x.data_ptr() for x in d_id], [x.data_ptr() for x in d_t], [x.data_ptr() for x in d_in],
+                               prof, (), [dict(profiles=d_prof[d].data_ptr(), point_stages=d_ps[d].data_ptr()) for d in range(nd)],
+                               chunk=8, owner=owner)
+        torch.cuda.synchronize()
+        assert st["chunks_done"].sum() == 8 and (owner >= 0).all()
+        got = np.stack([d_prof[owner[g]][:, g].cpu().numpy() for g in range(n)], axis=1)
+        assert np.array_equal(got, one["profiles"])
+        for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"):
+            host_free(out[k])
+    finally:
+        part.close()
