@@ -20,13 +20,15 @@
 #include "mag_bessel_coeffs.cuh"
 
 #define DET_FN __device__ __forceinline__
-// log, exp and the Bessel series are inlined ~45 / ~36 / ~10 times into k_profiles (770 KB of
-// code, instruction-cache bound: DESIGN.md section 7).  -DMAG_DET_NOINLINE builds them out of line
-// (same arithmetic; an experiment for the next round, default off).
-#ifdef MAG_DET_NOINLINE
-#define DET_BIG __device__ __noinline__
-#else
+// log, exp and the Bessel series are called from ~45 / ~36 / ~10 places of k_profiles.  Inlined
+// they make 770 KB of code and the profile phase instruction-cache bound (round 1: 2.7
+// stall_no_instruction per issue); out of line the results are bit-identical (same arithmetic,
+// --fmad=false) and the profile phase is 25 % faster (round 2: 84 vs 111 ms per 12 500 galaxies,
+// profiles/r2_bench.md).  -DMAG_DET_INLINE restores the inlined build for A/B runs.
+#ifdef MAG_DET_INLINE
 #define DET_BIG __device__ __forceinline__
+#else
+#define DET_BIG __device__ __noinline__
 #endif
 
 namespace detmath {

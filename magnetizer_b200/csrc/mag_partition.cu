@@ -27,8 +27,6 @@
 #include <thread>
 #include <vector>
 
-#include <cuda_runtime.h>
-
 #include "../../include/magnetizer_b200.h"
 
 namespace {

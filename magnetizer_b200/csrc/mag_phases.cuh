@@ -39,6 +39,8 @@ __device__ __constant__ const int REC_WS[R_COUNT] = {A_X, A_H, A_BEQ, A_RKPC, C_
 
 struct SnapRec {       // dense [ngal][nz]
   int32_t flags, nx, nx_pre, nx_mid, nsteps, status;
+  uint32_t gflags;     // MAG_FLAG_* raised by the profile phase up to and including this snapshot
+  int32_t pad;
   long long off;       // arena offset (doubles) of R_COUNT arrays, each `nx` long
   long long off_pre;   // arena offset of Beq on the pre-adjust grid [nx_pre] (SR_RESEED only)
   double dt, t_Gyr, lambda, delta_r_floor, tau_min, v_code;
@@ -46,7 +48,7 @@ struct SnapRec {       // dense [ngal][nz]
 struct GalHead {       // [chunk]
   int32_t init_it, max_it, error;
   uint32_t flags;
-  long long cost;      // sum over SR_SOLVE snapshots of nsteps*nx
+  long long cost;      // scheduling cost: sum over SR_SOLVE snapshots of nsteps*nx*(relative time per point of the one-warp loop)
   int32_t nx_max;      // largest grid of an SR_SOLVE snapshot
   int32_t pad;
 };
@@ -163,7 +165,7 @@ __device__ inline bool write_record(Gal& G, int it, int flags, int nx_pre, int n
   if (G.lane == 0) {
     SnapRec& R = a->recs[(size_t)(G.g - a->g0) * a->nz + it - 1];   // record tables are chunk-local
     R.flags = flags | SR_VALID; R.nx = nx; R.nx_pre = nx_pre; R.nx_mid = nx_mid; R.nsteps = G.nsteps;
-    R.status = (int)G.status; R.off = off; R.off_pre = off_pre;
+    R.status = (int)G.status; R.off = off; R.off_pre = off_pre; R.gflags = G.flags; R.pad = 0;
     R.dt = G.dt; R.t_Gyr = G.t_Gyr; R.lambda = G.lambda; R.delta_r_floor = G.delta_r_floor;
     R.tau_min = G.tau_min; R.v_code = G.v_code;
   }
@@ -256,7 +258,11 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
     set_timestep(G, true);
     if (!test_run && !elliptical) {
       fl |= SR_SOLVE;
-      H.cost += (long long)G.nsteps * G.nx;
+      // time of this snapshot on a one-warp team, in units of (steps x points) of the default grid: the
+      // large-grid variants of the warp loop stream their coefficients and are slower per point
+      // (measured, profiles/r1_bench.md: 177 / 117 / 77 G point-stages/s for nx <= 192 / 256 / 352)
+      const int w16 = G.nx <= 192 ? 16 : (G.nx <= 256 ? 24 : (G.nx <= 352 ? 37 : 64));
+      H.cost += (long long)G.nsteps * G.nx * w16 / 16;
       H.nx_max = max(H.nx_max, G.nx);
     }
     if (G.last_output) fl |= SR_LAST;
@@ -317,7 +323,9 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkSharedT<TEAM>* rs)
   (void)random_sign(G);
   G.refresh_sign = true;
   G.sign_nx = -1;
-  G.flags = H.flags; G.point_stages = 0;
+  // the diagnostic flags of the profile phase arrive with the snapshot records: a run that stops early
+  // (status 'i') must not report what the reference would only have met in later snapshots
+  G.flags = 0; G.point_stages = 0;
   G.t = 0; G.nsteps = 20;
   G.w0 = a->nz + 1; G.w1 = 0;
   G.init_it = H.init_it; G.max_it = H.max_it;
@@ -329,6 +337,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkSharedT<TEAM>* rs)
   for (int it = H.init_it; it <= H.max_it; it++) {
     const SnapRec R = recs[it - 1];
     if (!(R.flags & SR_VALID)) break;
+    G.flags |= R.gflags;
     bool ok = true;
     PHASE_BEGIN;
     if (R.flags & SR_TRAP) {

@@ -82,9 +82,6 @@ struct RkSharedT {
   // follow the short lines
   alignas(16) double pool[(2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM) > 1920 ? (2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM) : 1920];
   static_assert(2 * 3 * MAG_LINE_L(TEAM) <= 2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM, "RkShared pool too small for the long lines");
-#ifdef MAG_WARP_SMEM_EXCHANGE
-  alignas(16) double xch[2][3][32 * 6];   // build-time experiment (mag_rk_warp.cuh): halo exchange lines, 48-byte lane stride
-#endif
 };
 using RkShared = RkSharedT<MAG_TEAM_LIGHT>;   // the one-warp loop of mag_rk_warp.cuh
 

@@ -85,9 +85,6 @@ template <int PPL, int MODE>
 struct WarpState {
   double f[3][PPL], ft[3][PPL];
   double hl[3][3], hr[3][3];   // halo: the last 3 registers of lane-1, the first 3 of lane+1 (filled by warp_exchange)
-#ifdef MAG_WARP_SMEM_EXCHANGE
-  unsigned xaddr; int xbuf;    // shared address of RkShared::xch, current buffer
-#endif
   double w[MODE == WM_REGS ? PPL : 1][8];
   double ca[MODE == WM_ALLG ? 1 : PPL], gs[MODE == WM_ALLG ? 1 : PPL], c0[MODE == WM_ALLG ? 1 : PPL];
   double fk[MODE == WM_ALLG ? 1 : PPL], ak[MODE == WM_ALLG ? 1 : PPL];
@@ -293,10 +290,6 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
     for (int j = 0; j < PPL; j++) { B2[j] = S.f[1][j] * S.f[1][j]; bb[j] = S.f[0][j] * S.f[1][j]; }
 #pragma unroll
     for (int j = 0; j < PPL; j++) { h[j] = fma(-g[j], h[j], 0.5); B2[j] = fma(S.f[0][j], S.f[0][j], B2[j]); }
-#ifdef MAG_TRACK_B2   // staged for the next round: |B| bound from Br^2 + Bp^2 (>= +0: unsigned order of the high words)
-#pragma unroll
-    for (int j = 0; j < PPL; j++) mBu = max(mBu, (unsigned)__double2hiint(B2[j]));
-#endif
 #pragma unroll
     for (int j = 0; j < PPL; j++) { g[j] = fma(g[j], h[j], g[j]); B2[j] = al[j] * B2[j]; }
 #pragma unroll
@@ -352,59 +345,20 @@ __device__ __forceinline__ void warp_stage(WarpState<PPL, MODE>& S, const unsign
   for (int j = 0; j < PPL; j++) {
     S.f[0][j] = fma(dg, p0[j], S.ft[0][j]); S.f[1][j] = fma(dg, p1[j], S.ft[1][j]); S.f[2][j] = fma(dg, p2[j], S.ft[2][j]);
   }
-#ifdef MAG_WARP_SMEM_EXCHANGE
-  // Staged experiment for the next round (not validated on the GPU): exchange through two
-  // shared-memory lines instead of 36 shuffles -- (PPL+1)/2 stores and 4 loads per variable, a
-  // 48-byte lane stride keeps the 128-bit accesses conflict free, one __syncwarp per stage
-  // (the buffers alternate, so a lane that runs ahead never overwrites what another still reads).
-  constexpr bool kSmemX = PPL <= 6;
-  if (kSmemX) {
-    const unsigned base = S.xaddr + (unsigned)S.xbuf * (3u * 32u * 48u);
-    S.xbuf ^= 1;
-    const int lane_ = (int)(threadIdx.x & 31);
-#pragma unroll
-    for (int v = 0; v < 3; v++) {
-      const unsigned row = base + (unsigned)v * (32u * 48u) + (unsigned)lane_ * 48u;
-#pragma unroll
-      for (int j = 0; j + 1 < PPL; j += 2)
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row + 8u * j), "d"(S.f[v][j]), "d"(S.f[v][j + 1]) : "memory");
-      if (PPL % 2) asm volatile("st.shared.f64 [%0], %1;" ::"r"(row + 8u * (PPL - 1)), "d"(S.f[v][PPL - 1]) : "memory");
-    }
-    __syncwarp();
-#pragma unroll
-    for (int v = 0; v < 3; v++) {
-      const unsigned lrow = base + (unsigned)v * (32u * 48u) + (unsigned)max(lane_ - 1, 0) * 48u + 8u * (PPL - 3);
-      const unsigned rrow = base + (unsigned)v * (32u * 48u) + (unsigned)min(lane_ + 1, 31) * 48u;
-      if ((PPL - 3) % 2) {   // first of the three is 8-byte aligned only
-        S.hl[v][0] = lds_f64x(lrow);
-        const double2 t = lds_pair(lrow + 8u); S.hl[v][1] = t.x; S.hl[v][2] = t.y;
-      } else {
-        const double2 t = lds_pair(lrow); S.hl[v][0] = t.x; S.hl[v][1] = t.y;
-        S.hl[v][2] = lds_f64x(lrow + 16u);
-      }
-      const double2 t = lds_pair(rrow); S.hr[v][0] = t.x; S.hr[v][1] = t.y;
-      S.hr[v][2] = lds_f64x(rrow + 16u);
-    }
-  }
-#else
-  constexpr bool kSmemX = false;
-#endif
   // the new state is final: the halo exchange for the next stage starts now; its 36 shuffles
   // (one issue slot every ~4 cycles) are interleaved with the ftmp update and the maxima
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
 #pragma unroll
     for (int v = 0; v < 3; v++) {
-      if (!kSmemX && j < 3) S.hr[v][j] = shfl_down1(S.f[v][j]);
-      if (!kSmemX && j >= PPL - 3) S.hl[v][j - (PPL - 3)] = shfl_up1(S.f[v][j]);
+      if (j < 3) S.hr[v][j] = shfl_down1(S.f[v][j]);
+      if (j >= PPL - 3) S.hl[v][j - (PPL - 3)] = shfl_up1(S.f[v][j]);
       if (LAST) S.ft[v][j] = S.f[v][j];
       else S.ft[v][j] = fma(dz, v == 0 ? p0[j] : (v == 1 ? p1[j] : p2[j]), S.f[v][j]);
     }
     // |x| maxima on the high words: signed max catches the positive values, unsigned max the negative ones
-#ifndef MAG_TRACK_B2
     mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(S.f[0][j]), __double2hiint(S.f[1][j]));
     mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(S.f[0][j]), (unsigned)__double2hiint(S.f[1][j]));
-#endif
     mAs = (unsigned)max((int)mAs, __double2hiint(S.f[2][j]));
     mAu = max(mAu, (unsigned)__double2hiint(S.f[2][j]));
   }
@@ -437,11 +391,6 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
   double2* const wt2 = reinterpret_cast<double2*>(rs->pool) + lane;                          // shared pair table, this lane's column
   double2* const tab = reinterpret_cast<double2*>(W + (size_t)WARP_TABLE_ARRAY * nxcap) + lane;   // global pair table
   const unsigned wsa = (unsigned)__cvta_generic_to_shared(rs->pool) + 16u * lane;
-#ifdef MAG_WARP_SMEM_EXCHANGE
-#define MAG_WARP_SMEM_EXCHANGE_INIT(S) do { (S).xaddr = (unsigned)__cvta_generic_to_shared(rs->xch); (S).xbuf = 0; } while (0)
-#else
-#define MAG_WARP_SMEM_EXCHANGE_INIT(S) do {} while (0)
-#endif
 
   PHASE_BEGIN;
   prepare_fast_coefs(G, nx);
@@ -452,7 +401,6 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
   PHASE_END(5, lane);
 
   WarpState<PPL, MODE> S;
-  MAG_WARP_SMEM_EXCHANGE_INIT(S);
 #pragma unroll
   for (int j = 0; j < PPL; j++) {
     const int g = g0 + j;
@@ -556,10 +504,8 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
     unsigned mBs = 0, mBu = 0, mAs = 0, mAu = 0;   // running maxima start from the block's initial state
 #pragma unroll
     for (int j = 0; j < PPL; j++) {
-#ifndef MAG_TRACK_B2   // (with MAG_TRACK_B2 the first stage of the block sees this state as its input)
       mBs = (unsigned)__vimax3_s32((int)mBs, __double2hiint(S.f[0][j]), __double2hiint(S.f[1][j]));
       mBu = __vimax3_u32(mBu, (unsigned)__double2hiint(S.f[0][j]), (unsigned)__double2hiint(S.f[1][j]));
-#endif
       mAs = (unsigned)max((int)mAs, __double2hiint(S.f[2][j]));
       mAu = max(mAu, (unsigned)__double2hiint(S.f[2][j]));
     }
@@ -611,17 +557,7 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
     }
     // ---- accept or replay the block.  Per-lane maxima of lanes 0,1 / tm-1,tm bound the 7 points
     // next to the inner / outer boundary (a superset of them: conservative).
-#ifdef MAG_TRACK_B2
-    // the stages tracked Br^2 + Bp^2 of their INPUT states; add the final state of the block, then
-    // turn the bound on B^2 into one on |B| (one ulp of slack on the high word each way)
-#pragma unroll
-    for (int j = 0; j < PPL; j++) mBu = max(mBu, (unsigned)__double2hiint(fma(S.f[0][j], S.f[0][j], S.f[1][j] * S.f[1][j])));
-    const unsigned mB = mBu >= 0x7fe00000u ? mBu : (unsigned)__double2hiint(sqrt(__hiloint2double((int)mBu + 1, 0)));
-    const unsigned mA = max(mAs, mAu & 0x7fffffffu);
-    (void)mBs;
-#else
     const unsigned mB = max(mBs, mBu & 0x7fffffffu), mA = max(mAs, mAu & 0x7fffffffu);
-#endif
     const unsigned nB0 = max(__shfl_sync(FULL, mB, 0), __shfl_sync(FULL, mB, 1));
     const unsigned nA0 = max(__shfl_sync(FULL, mA, 0), __shfl_sync(FULL, mA, 1));
     const unsigned nB1 = max(__shfl_sync(FULL, mB, tm), __shfl_sync(FULL, mB, tm - 1));

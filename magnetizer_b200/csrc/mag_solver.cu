@@ -160,7 +160,8 @@ __global__ void __maxnreg__(MAG_HEAVY_MAXREG) k_evolve_heavy(KernelArgs a) {
 }
 
 // ------------------------------------------------------------------ cost-ordered queues
-// Exact cost = sum of nsteps*nx, known after Phase A.  `order` = heavy class first, then the
+// The cost of every history (sum of nsteps*nx, weighted by the speed of the loop variant its grids
+// take) is exact after Phase A.  `order` = heavy class first, then the
 // light class, each longest-first (counting sort on 1/16-octave buckets of the cost).  A
 // galaxy is heavy when its history alone would keep one warp busy for longer than `alpha`
 // times the fair share of a warp slot (sum of all costs / number of slots): under a
@@ -270,10 +271,10 @@ struct mag_ctx {
   double last_ms[4] = {0, 0, 0, 0};
   int last_launches = 0;
   int use_fast = 1;
-  int launch_pdl = 0;         // 1: light kernel as programmatic dependent of the heavy one, 0: two streams
+  int launch_pdl = 1;         // 1: light kernel as programmatic dependent of the heavy one, 0: two streams
   int stage_profile_rows = 1; // rows of the profile phase: HBM + one copy per plane during k_evolve (0: zero-copy stores)
   QueuePolicy policy;
-  double heavy_alpha = 0.6;
+  double heavy_alpha = 0.8;
   PendingCall pend;
 };
 
@@ -347,7 +348,7 @@ static int create_impl(mag_ctx* c, const cudaDeviceProp& prop) {
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
   c->split_chains = env_int("MAG_INLINE_CHAINS", 0) ? 0 : 1;
   c->use_fast = env_int("MAG_DISABLE_FAST_PATH", 0) ? 0 : 1;
-  c->launch_pdl = env_int("MAG_EVOLVE_PDL", 0);
+  c->launch_pdl = env_int("MAG_EVOLVE_PDL", 1);
   c->stage_profile_rows = env_int("MAG_STAGE_PROFILE_ROWS", 1);
   c->policy.mode = env_int("MAG_HEAVY_MODE", 1);
   c->policy.nx_heavy = env_int("MAG_HEAVY_NX", 352);

@@ -124,22 +124,62 @@ struct Namelist {
   bool get(const std::string& key, std::string* v) const { auto p = find(key); if (!p) return false; *v = (*p)[0]; return true; }
 };
 
-// I/O settings of io_parameters the driver needs (global_input_parameters.f90:30-62)
+// I/O and run-control settings the driver needs (global_input_parameters.f90:30-91)
 struct RunConfig {
   mag_params_t params;
-  std::string model_name = "Magnetizer run";
-  std::string input_file_name, output_file_name;
+  std::string model_name = "Magnetized SAM";
+  std::string input_file_name = "magnetized_galaxies_input.hdf5", output_file_name = "magnetized_galaxies_output.hdf5";
   std::vector<std::string> output_quantities_list;
   int info = 1;
+  // io_parameters: dataset storage and checkpoint cadence (IO_hdf5.f90:940-981, distributor.f90:299-336)
+  int p_IO_chunking = 1, p_IO_number_of_galaxies_in_chunks = 1000, p_IO_compression = 1, p_IO_compression_level = 6;
+  int p_ncheckpoint = 5000;
+  double p_max_walltime = -1;   // seconds; < 0: no limit (run_parameters, :85)
+  std::vector<std::string> warnings;   // unknown keys, keys without effect on this path
 };
+
+// Every key of the reference's seven namelists that is NOT a member of mag_params_t, with what
+// a non-default value means here.  A switch the CUDA path does not implement must keep its
+// default: anything else would run default physics under a non-default label (the effective
+// parameters are stamped into the output file), so it is an error, not a warning.
+struct OtherKey { const char* name; const char* dflt; int kind; };   // kind 0: must equal dflt, 1: no effect on this path
+static const OtherKey kOtherKeys[] = {
+    // dynamo_parameters
+    {"alp_ceiling", ".true.", 0}, {"alp_squared", ".false.", 0}, {"krause", ".true.", 0}, {"advect", ".true.", 0},
+    {"turb_dif", ".true.", 0}, {"p_neumann_boundary_condition_rmax", ".false.", 0},
+    {"p_r_seed_decay", "15.0", 1}, {"p_nn_seed", "2", 1},   // only read by the seed choices that are rejected anyway
+    // grid_parameters
+    {"p_rescale_field_for_shrinking_disks", ".true.", 0}, {"p_rescale_field_for_expanding_disks", ".false.", 0},
+    {"p_scale_back_f_array", ".true.", 0}, {"p_use_fixed_physical_grid", ".false.", 0}, {"p_interp_method", "simple", 0},
+    // ISM_and_disk_parameters
+    {"p_check_hydro_solution", ".false.", 1}, {"p_use_fixed_turbulent_to_scaleheight_ratio", ".false.", 0},
+    {"p_turbulent_to_scaleheight_ratio", "0.25", 1}, {"p_truncates_within_rreg", ".false.", 0},
+    {"p_extra_pressure_outputs", ".false.", 0}, {"p_p2_workaround", ".false.", 0}, {"p_sech2_profile", ".false.", 0},
+    {"p_pdm_numerical", ".false.", 0}, {"p_pbulge_numerical", ".false.", 0},
+    // run_parameters / io_parameters
+    {"p_onesnaphotdebugmode", ".false.", 0}, {"output_everything", ".false.", 0}, {"p_io_separate_output", ".true.", 0},
+    {"p_master_works_too", ".false.", 1}, {"p_master_skip", "2", 1},   // MPI farm details: replaced by the GPU partition
+    // observables_parameters: another executable (Observables.f90)
+    {"p_obs_cr_alpha", "", 1}, {"p_obs_dust_alpha", "", 1}, {"p_obs_ignore_small_scale", "", 1}, {"p_obs_scale_with_z", "", 1},
+    {"p_obs_redshift_indices", "", 1}, {"p_obs_use_all_redshifts", "", 1},
+};
+
+inline bool same_value(const std::string& a0, const std::string& b0) {
+  const std::string a = Namelist::lower(a0), b = Namelist::lower(b0);
+  if (a == b) return true;
+  try { return Namelist::to_bool(a) == Namelist::to_bool(b); } catch (...) {}
+  try { return Namelist::to_double(a) == Namelist::to_double(b); } catch (...) {}
+  return false;
+}
 
 inline RunConfig load_run_config(const std::string& path) {
   RunConfig rc;
   mag_params_default(&rc.params);
   const Namelist nl = Namelist::parse_file(path);
   mag_params_t& p = rc.params;
+  std::map<std::string, bool> known;
   // every mag_params_t member has the name of the reference's namelist variable
-#define MAG_NL(field) nl.get(#field, &p.field)
+#define MAG_NL(field) (known[Namelist::lower(#field)] = true, nl.get(#field, &p.field))
   MAG_NL(nsteps_0); MAG_NL(p_nsteps_max); MAG_NL(p_MAX_FAILS); MAG_NL(p_random_seed); MAG_NL(p_no_magnetic_fields_test_run);
   MAG_NL(p_courant_v); MAG_NL(p_courant_eta); MAG_NL(p_nx_ref); MAG_NL(p_nx_MAX); MAG_NL(p_rmax_over_rdisk);
   MAG_NL(frac_seed); MAG_NL(C_alp); MAG_NL(C_floor); MAG_NL(p_floor_kappa); MAG_NL(fmag); MAG_NL(R_kappa);
@@ -151,15 +191,44 @@ inline RunConfig load_run_config(const std::string& path) {
   MAG_NL(p_variable_timesteps); MAG_NL(p_simplified_pressure); MAG_NL(p_halo_contraction); MAG_NL(p_enable_P2);
   MAG_NL(Dyn_quench); MAG_NL(Alg_quench); MAG_NL(Damp); MAG_NL(lFloor); MAG_NL(p_space_varying_floor);
   MAG_NL(p_time_varying_floor); MAG_NL(p_limit_turbulent_scale); MAG_NL(p_allow_positive_shears);
+  MAG_NL(p_outflow_Lsn); MAG_NL(p_outflow_fOB); MAG_NL(p_outflow_etaSN); MAG_NL(p_tOB); MAG_NL(p_N_SN1OB);
+  MAG_NL(p_outflow_hot_gas_density); MAG_NL(p_outflow_nu0); MAG_NL(p_outflow_alphahot); MAG_NL(p_outflow_Vhot);
 #undef MAG_NL
   std::string s;
   if (nl.get("p_seed_choice", &s)) p.seed_choice = (Namelist::lower(s) == "random") ? 0 : 1;
-  if (nl.get("p_outflow_type", &s)) p.outflow_type = (Namelist::lower(s) == "no_outflow") ? 0 : 1;
+  if (nl.get("p_outflow_type", &s)) {
+    static const char* names[] = {"no_outflow", "vturb", "wind", "superbubble_simple", "superbubble"};
+    p.outflow_type = -1;   // unknown prescription: mag_create rejects it (outflow.f90:92-94 stops)
+    for (int k = 0; k < 5; k++) if (Namelist::lower(s) == names[k]) p.outflow_type = k;
+  }
   nl.get("model_name", &rc.model_name);
   nl.get("input_file_name", &rc.input_file_name);
   nl.get("output_file_name", &rc.output_file_name);
   nl.get("info", &rc.info);
+  nl.get("p_IO_chunking", &rc.p_IO_chunking);
+  nl.get("p_IO_number_of_galaxies_in_chunks", &rc.p_IO_number_of_galaxies_in_chunks);
+  nl.get("p_IO_compression", &rc.p_IO_compression);
+  nl.get("p_IO_compression_level", &rc.p_IO_compression_level);
+  nl.get("p_ncheckpoint", &rc.p_ncheckpoint);
+  nl.get("p_max_walltime", &rc.p_max_walltime);
   if (auto q = nl.find("output_quantities_list")) rc.output_quantities_list = *q;
+  for (const char* k : {"p_seed_choice", "p_outflow_type", "model_name", "input_file_name", "output_file_name", "info", "p_io_chunking",
+                        "p_io_number_of_galaxies_in_chunks", "p_io_compression", "p_io_compression_level", "p_ncheckpoint",
+                        "p_max_walltime", "output_quantities_list"})
+    known[Namelist::lower(k)] = true;
+  // keys outside mag_params_t: unimplemented switches must keep their defaults
+  for (const OtherKey& ok : kOtherKeys) {
+    known[ok.name] = true;
+    const auto* v = nl.find(ok.name);
+    if (!v) continue;
+    if (ok.kind == 0 && !same_value((*v)[0], ok.dflt))
+      throw std::runtime_error(std::string("parameter file sets ") + ok.name + " = " + (*v)[0] +
+                               ": this switch is not implemented by the CUDA path and must keep its default (" + ok.dflt + ")");
+    if (ok.kind == 1) rc.warnings.push_back(std::string(ok.name) + " has no effect on the dynamo path");
+  }
+  for (const auto& g : nl.groups)
+    for (const auto& kv : g.second)
+      if (!known.count(kv.first)) rc.warnings.push_back("unknown key " + kv.first + " in &" + g.first + " ignored");
   return rc;
 }
 

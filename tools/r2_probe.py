@@ -54,7 +54,7 @@ def main():
     s = S.DynamoSolver(device=0)
     print(s.info(), flush=True)
 
-    def modes(tag, ids, inp, alphas=(0.6,)):
+    def modes(tag, ids, inp, alphas=(0.8,)):
         out = s.alloc_outputs(len(ids), t.size, PROF, SCAL, pinned=True)
         ref = None
         for name, mode, alpha in [("light only", 0, 0.0)] + [(f"split alpha={a}", 1, a) for a in alphas] + [("heavy only", 2, 0.0)]:
@@ -68,22 +68,26 @@ def main():
                 same = all(np.array_equal(ref[k], snap[k]) for k in ("nsteps", "point_stages"))
                 err = np.abs(ref["profiles"] - snap["profiles"]).max()
                 print(f"      vs light only: exact fields {'identical' if same else 'DIFFER'}, max abs profile difference {err:.2e}", flush=True)
-        s.set_heavy_policy(mode=1, alpha=0.6)
+        s.set_heavy_policy(mode=1, alpha=0.8)
 
     if "cfg2" in cases:
         ids = np.arange(1, base.shape[1] + 1, dtype=np.int32)
-        modes("config 2 (196 example galaxies)", ids, base, alphas=(0.3, 0.6, 1.0, 2.0))
+        modes("config 2 (196 example galaxies)", ids, base, alphas=(0.5, 0.8, 1.2))
     if "share" in cases:
         n = 12500
         syn = synthetic_histories(base, n, first=20000)
         ids = galaxy_ids(n, first=20000)
-        modes("config 3 share (12500 synthetic)", ids, syn, alphas=(0.3, 0.6, 1.0))
-        os.environ["MAG_EVOLVE_PDL"] = "1"
+        modes("config 3 share (12500 synthetic)", ids, syn, alphas=(0.4, 0.6, 0.8, 1.0, 1.3))
+        os.environ["MAG_EVOLVE_PDL"] = "0"
         s2 = S.DynamoSolver(device=0)
         del os.environ["MAG_EVOLVE_PDL"]
         r, tm, wall = timed(s2, ids, t, syn)
-        report("config 3 share split alpha=0.6, PDL launch", s2, r, tm, wall, n)
+        report("config 3 share split alpha=0.8, two streams", s2, r, tm, wall, n)
         s2.close()
+        n = 25000
+        syn = synthetic_histories(base, n, first=40000)
+        ids = galaxy_ids(n, first=40000)
+        modes("25000 synthetic", ids, syn, alphas=(0.8,))
     if "tput" in cases:
         for copies in (1, 148, 444, 1184):
             inp = np.ascontiguousarray(np.repeat(base[:, 4:5, :], copies, axis=1))
@@ -94,12 +98,12 @@ def main():
                 s.set_heavy_policy(mode=mode)
                 r, tm, wall = timed(s, ids, t, inp)
                 report(f"uniform gal 5 x{copies} (3 snapshots) {name}", s, r, tm, wall, copies)
-        s.set_heavy_policy(mode=1, alpha=0.6)
+        s.set_heavy_policy(mode=1, alpha=0.8)
     if "big" in cases:
         n = 40000
         syn = synthetic_histories(base, n)
         ids = galaxy_ids(n)
-        modes("40000 synthetic", ids, syn, alphas=(0.6,))
+        modes("40000 synthetic", ids, syn, alphas=(0.8,))
     if "variants" in cases and os.environ.get("MAG_PROBE_LIBS"):
         n = 512
         syn = synthetic_histories(base, n, first=30000)
