@@ -148,36 +148,28 @@ def ncu_metrics():
 
 def run_b200(args):
     import torch
-    import torch.distributed as dist
+    from magnetizer_b200.rendezvous import Rendezvous
     from magnetizer_b200.solver import DynamoSolver, Partition, host_array, host_free
     from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    gloo = None
+    rv = Rendezvous(backend="nccl", device=dev)      # NCCL carries one all-reduce at start-up, nothing on the solve path
+    world = rv.world
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(hours=2))
-        one = torch.ones(1, device=dev)
-        dist.all_reduce(one)                       # NCCL is up on every rank (it carries nothing else: no collective on the solve path)
-        assert int(one.item()) == world
-        gloo = dist.new_group(backend="gloo", timeout=datetime.timedelta(hours=2))   # host-side barrier: waiting ranks do not spin on their GPU
+        assert rv.check_backend(dev) == world
 
     def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier(group=gloo)
+        rv.barrier(sync=torch.cuda.synchronize)
 
-    if rank != 0:
+    if not rv.is_driver:
         # the partition is driven from rank 0 (one host process, one thread pair per GPU); the other
         # ranks keep the rendezvous: around the timed regions and at the end
-        for _ in range(5):
-            barrier()
-        dist.destroy_process_group()
+        rv.follow(5, sync=torch.cuda.synchronize)
+        rv.close()
         return
 
     ndev = world
@@ -370,8 +362,7 @@ def run_b200(args):
     for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"):
         host_free(out[k])
     barrier()
-    if world > 1:
-        dist.destroy_process_group()
+    rv.close()
 
 
 def main():

@@ -43,7 +43,14 @@ namespace magdev {
 // it when the rest of the batch is done (the tail of the cost-ordered queue), and for grids the
 // warp loop does not take (p_nx_ref = 401 of BASELINE config 5).
 #define MAG_TEAM_LIGHT 32
+#ifndef MAG_TEAM_HEAVY
 #define MAG_TEAM_HEAVY 128
+#endif
+// points per thread up to which the stencil weights of a team loop live in shared memory (above: the
+// streaming variant); sets the size of a team's shared memory and with it the teams per SM
+#ifndef MAG_WSMEM_SLOTS
+#define MAG_WSMEM_SLOTS 4
+#endif
 #define MAG_FAST_MAXPPL 8     // fast path up to nx = 8 * TEAM
 #define MAG_LINE_S(TEAM) (4 * (TEAM) + 8)   // shared line of the PPL <= 4 variants
 #define MAG_LINE_L(TEAM) (8 * (TEAM) + 8)   // shared line of the PPL = 8 variant
@@ -80,8 +87,8 @@ struct RkSharedT {
   // (4 pad points each side, so that a thread's window -- own points +-3 -- is covered by
   // 16-byte aligned vector loads); for COEF_WSMEM the stencil weights [k][slot*64 + thread]
   // follow the short lines
-  alignas(16) double pool[(2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM) > 1920 ? (2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM) : 1920];
-  static_assert(2 * 3 * MAG_LINE_L(TEAM) <= 2 * 3 * MAG_LINE_S(TEAM) + 8 * 4 * TEAM, "RkShared pool too small for the long lines");
+  alignas(16) double pool[(2 * 3 * MAG_LINE_S(TEAM) + 8 * MAG_WSMEM_SLOTS * TEAM) > 1920 ? (2 * 3 * MAG_LINE_S(TEAM) + 8 * MAG_WSMEM_SLOTS * TEAM) : 1920];
+  static_assert(2 * 3 * MAG_LINE_L(TEAM) <= 2 * 3 * MAG_LINE_S(TEAM) + 8 * MAG_WSMEM_SLOTS * TEAM || 2 * 3 * MAG_LINE_L(TEAM) <= 1920, "RkShared pool too small for the long lines");
 };
 using RkShared = RkSharedT<MAG_TEAM_LIGHT>;   // the one-warp loop of mag_rk_warp.cuh
 
@@ -264,8 +271,8 @@ __device__ __forceinline__ void fast_stage(FastState<PPL, MODE>& S, RkSharedT<TE
     double w[7], w0a, c_ca, c_gs, c_fb, c_kdc, c_p3, c_qc, c_ak;
     if (MODE == COEF_WSMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) w[k] = wts[(k * 4 + j) * TEAM + tid];
-      w0a = wts[(7 * 4 + j) * TEAM + tid];
+      for (int k = 0; k < 7; k++) w[k] = wts[(k * MAG_WSMEM_SLOTS + j) * TEAM + tid];
+      w0a = wts[(7 * MAG_WSMEM_SLOTS + j) * TEAM + tid];
     } else if (MODE == COEF_REGS) {
 #pragma unroll
       for (int k = 0; k < 7; k++) w[k] = S.w[MODE == COEF_REGS ? j : 0][k];
@@ -410,8 +417,8 @@ __device__ __noinline__ void fast_loop_team(Gal* G, RkSharedT<TEAM>* rs) {
     const int g = tid * PPL + j;
     if (MODE == COEF_WSMEM) {
 #pragma unroll
-      for (int k = 0; k < 7; k++) wts[(k * 4 + j) * TEAM + tid] = WA(C_W0 + k)[g];
-      wts[(7 * 4 + j) * TEAM + tid] = WA(C_W0A)[g];
+      for (int k = 0; k < 7; k++) wts[(k * MAG_WSMEM_SLOTS + j) * TEAM + tid] = WA(C_W0 + k)[g];
+      wts[(7 * MAG_WSMEM_SLOTS + j) * TEAM + tid] = WA(C_W0A)[g];
     } else if (MODE == COEF_REGS) {
 #pragma unroll
       for (int k = 0; k < 7; k++) S.w[MODE == COEF_REGS ? j : 0][k] = WA(C_W0 + k)[g];
@@ -608,7 +615,9 @@ __device__ __forceinline__ void fast_dispatch(Gal* G, RkSharedT<TEAM>* rs) {
     case 1: if (TEAM > 32) fast_loop_team<TEAM, 1, COEF_REGS>(G, rs); break;   // (one-warp teams: nx >= 64 has PPL >= 2)
     case 2: fast_loop_team<TEAM, 2, COEF_REGS>(G, rs); break;
     case 3: fast_loop_team<TEAM, 3, COEF_WSMEM>(G, rs); break;
+#if MAG_WSMEM_SLOTS >= 4
     case 4: fast_loop_team<TEAM, 4, COEF_WSMEM>(G, rs); break;
+#endif
     default: fast_loop_team<TEAM, 8, COEF_GLOBAL>(G, rs); break;
   }
 }
@@ -625,7 +634,7 @@ __device__ bool run_timesteps(Gal& G, RkSharedT<TEAM>* rs) {
     if (G.lane == 0) {
       FastCall& C = rs->call;
       C.W = G.W; C.nxcap = G.a->nxcap; C.nx = G.nx; C.nsteps = G.nsteps;
-      C.ppl = (TEAM > 32 && G.nx <= TEAM) ? 1 : (G.nx <= 2 * TEAM ? 2 : (G.nx <= 3 * TEAM ? 3 : (G.nx <= 4 * TEAM ? 4 : 8)));
+      C.ppl = (TEAM > 32 && G.nx <= TEAM) ? 1 : (G.nx <= 2 * TEAM ? 2 : (G.nx <= 3 * TEAM ? 3 : ((MAG_WSMEM_SLOTS >= 4 && G.nx <= 4 * TEAM) ? 4 : 8)));
       C.sign_nx = G.sign_nx; C.refresh_sign = G.refresh_sign ? 1 : 0; C.cmd = TEAM_CMD_FAST; C.ok = 1;
       C.dt = G.dt; C.t = G.t; C.t_Gyr = G.t_Gyr; C.dtg = G.dt * G.a->U.t0_Gyr;
       C.tau_min_kappa = G.a->P.p_floor_kappa * G.tau_min; C.t_last_sign_choice = G.t_last_sign_choice;

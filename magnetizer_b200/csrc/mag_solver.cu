@@ -274,7 +274,7 @@ struct mag_ctx {
   int launch_pdl = 1;         // 1: light kernel as programmatic dependent of the heavy one, 0: two streams
   int stage_profile_rows = 1; // rows of the profile phase: HBM + one copy per plane during k_evolve (0: zero-copy stores)
   QueuePolicy policy;
-  double heavy_alpha = 0.8;
+  double heavy_alpha = 1.5;
   PendingCall pend;
 };
 

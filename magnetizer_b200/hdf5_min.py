@@ -19,8 +19,15 @@ _UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
 class H5Dataset:
-    def __init__(self, f, shape, dtype, layout, filters, attrs):
+    def __init__(self, f, shape, dtype, layout, filters, attrs, fill=None):
         self._f, self.shape, self.dtype, self._layout, self._filters, self.attrs = f, shape, dtype, layout, filters, attrs
+        self._fill = fill
+
+    def _empty(self):
+        out = np.zeros(self.shape, self.dtype)
+        if self._fill is not None and len(self._fill) == np.dtype(self.dtype).itemsize:
+            out[...] = np.frombuffer(self._fill, self.dtype)[0]
+        return out
 
     def read(self) -> np.ndarray:
         f = self._f
@@ -29,12 +36,12 @@ class H5Dataset:
             _, addr, size = self._layout
             n = int(np.prod(self.shape)) if self.shape else 1
             if addr == _UNDEF:
-                return np.zeros(self.shape, self.dtype)
+                return self._empty()
             return np.frombuffer(f.buf, self.dtype, n, addr).reshape(self.shape).copy()
         if kind == "compact":
             return np.frombuffer(self._layout[1], self.dtype).reshape(self.shape).copy()
         _, btree, cdims = self._layout
-        out = np.zeros(self.shape, self.dtype)
+        out = self._empty()
         if btree == _UNDEF:
             return out
         nd = len(self.shape)
@@ -192,9 +199,17 @@ class H5File:
     # ------------------------------------------------------------------ public
     def _open(self, ohdr):
         msgs = self._messages(ohdr)
-        attrs, shape, dtype, layout, filters, stab = {}, None, None, None, [], None
+        attrs, shape, dtype, layout, filters, stab, fill = {}, None, None, None, [], None, None
         for mtype, body, msize, _ in msgs:
-            if mtype == 0x01:
+            if mtype == 0x05:   # fill value (versions 1-3): what never-written chunks read as
+                ver = self.buf[body]
+                if ver in (1, 2) and (ver == 1 or self.buf[body + 3]):
+                    sz = self._u("I", body + 4)[0]
+                    fill = bytes(self.buf[body + 8:body + 8 + sz])
+                elif ver == 3 and self.buf[body + 1] & 0x20:
+                    sz = self._u("I", body + 2)[0]
+                    fill = bytes(self.buf[body + 6:body + 6 + sz])
+            elif mtype == 0x01:
                 shape = self._parse_dataspace(body)
             elif mtype == 0x03:
                 dtype = self._parse_dtype(body)
@@ -237,7 +252,7 @@ class H5File:
                 stab = self._u("QQ", body)
         if stab is not None:
             return ("group", self._group_entries(*stab), attrs)
-        return ("dataset", H5Dataset(self, shape, dtype, layout, filters, attrs), attrs)
+        return ("dataset", H5Dataset(self, shape, dtype, layout, filters, attrs, fill), attrs)
 
     def attrs(self, path="/"):
         return self._resolve(path)[2]

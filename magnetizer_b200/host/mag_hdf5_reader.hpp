@@ -3,26 +3,57 @@
 // python/prepare_input.py:93-150 of the reference, read on the Fortran side by
 // IO_read_dataset_scalar, source/IO_hdf5.f90:365-460): superblock v0, v1 object headers,
 // symbol-table groups (v1 B-tree + local heap), contiguous or chunked (v1 chunk B-tree)
-// datasets of f32/f64/integers, deflate and shuffle filters.  Values are returned as double.
+// datasets of f32/f64/integers, deflate and shuffle filters, fill values.  Values are returned as
+// double.  The file is memory-mapped, so that the driver can look into an output file of any size
+// when it resumes a run (Log/completed, the chunk lists of the datasets it extends).
 #pragma once
 #include <cstdint>
 #include <cstring>
-#include <fstream>
 #include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+
+#include "mag_hdf5_writer.hpp"   // H5ChunkRec
 
 namespace maghost {
 
+// read-only memory map of a whole file
+class FileMap {
+ public:
+  explicit FileMap(const std::string& path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("cannot open " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); throw std::runtime_error("cannot stat " + path); }
+    size_ = (size_t)st.st_size;
+    if (size_ > 0) {
+      void* p = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (p == MAP_FAILED) { ::close(fd); throw std::runtime_error("cannot map " + path); }
+      data_ = (const char*)p;
+    }
+    ::close(fd);
+  }
+  ~FileMap() { if (data_) munmap((void*)data_, size_); }
+  FileMap(const FileMap&) = delete;
+  FileMap& operator=(const FileMap&) = delete;
+  size_t size() const { return size_; }
+  const char* data() const { return data_; }
+  const char& operator[](size_t i) const { return data_[i]; }
+ private:
+  const char* data_ = nullptr;
+  size_t size_ = 0;
+};
+
 class H5Reader {
  public:
-  explicit H5Reader(const std::string& path) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) throw std::runtime_error("cannot open " + path);
-    buf_.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+  explicit H5Reader(const std::string& path) : buf_(path) {
     static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
     if (buf_.size() < 96 || std::memcmp(buf_.data(), sig, 8) != 0) throw std::runtime_error(path + ": not an HDF5 file");
     if (buf_[8] != 0) throw std::runtime_error("HDF5 superblock version not supported");
@@ -36,7 +67,26 @@ class H5Reader {
   };
 
   // dataset by path, e.g. "Input/r_disk"
-  Data read(const std::string& path) const {
+  Data read(const std::string& path) const { return read_dataset(locate(path), 0, UNDEF); }
+  // rows [g0, g0+n) of the first dimension only (the chunks that overlap them are decoded)
+  Data read_rows(const std::string& path, uint64_t g0, uint64_t n) const { return read_dataset(locate(path), g0, n); }
+  bool exists(const std::string& path) const {
+    try { locate(path); return true; } catch (const std::exception&) { return false; }
+  }
+  std::vector<uint64_t> shape(const std::string& path) const { return locate(path).shape; }
+  // file address of a contiguous dataset's storage (UNDEF for chunked ones)
+  uint64_t contiguous_address(const std::string& path) const { const Node n = locate(path); return n.layout == 1 ? n.addr : UNDEF; }
+  // the stored chunks of a chunked dataset (empty for contiguous ones): what a writer that extends the file adopts
+  std::vector<H5ChunkRec> chunks(const std::string& path) const {
+    const Node n = locate(path);
+    std::vector<H5ChunkRec> out;
+    if (n.layout == 2 && n.addr != UNDEF) list_chunks(n, n.addr, &out);
+    return out;
+  }
+
+ private:
+  struct Node;
+  Node locate(const std::string& path) const {
     uint64_t oh = root_ohdr_;
     size_t p = 0;
     while (p < path.size()) {
@@ -53,11 +103,10 @@ class H5Reader {
     }
     const Node n = open(oh);
     if (n.is_group) throw std::runtime_error(path + " is a group");
-    return read_dataset(n);
+    return n;
   }
 
- private:
-  std::vector<char> buf_;
+  FileMap buf_;
   uint64_t root_ohdr_ = 0;
   static constexpr uint64_t UNDEF = 0xFFFFFFFFFFFFFFFFull;
 
@@ -78,6 +127,8 @@ class H5Reader {
     std::vector<uint32_t> cdims;
     std::vector<int> filters;
     std::vector<uint32_t> shuffle_elem;
+    bool has_fill = false;
+    double fill = 0.0;
   };
 
   Node open(uint64_t ohdr) const {
@@ -114,6 +165,20 @@ class H5Reader {
               n.addr = u64(body + 3);
               for (int i = 0; i + 1 < nd1; i++) n.cdims.push_back(u32(body + 11 + 4 * i));
             } else throw std::runtime_error("compact datasets not supported");
+            break;
+          }
+          case 0x05: {  // fill value, versions 1-2 (version 3 packs the fields into flag bits)
+            const int ver = u8(body);
+            if (ver == 1 || ver == 2) {
+              const bool defined = ver == 1 ? true : u8(body + 3) != 0;
+              if (defined) {
+                const uint32_t sz = u32(body + 4);
+                if (sz == 8) { n.has_fill = true; std::memcpy(&n.fill, &buf_[body + 8], 8); }
+              }
+            } else if (ver == 3) {
+              const int flags = u8(body + 1);
+              if ((flags & 0x20) && u32(body + 2) == 8) { n.has_fill = true; std::memcpy(&n.fill, &buf_[body + 6], 8); }
+            }
             break;
           }
           case 0x0B: {  // filter pipeline
@@ -178,7 +243,26 @@ class H5Reader {
     throw std::runtime_error("HDF5 datatype not supported");
   }
 
-  void chunk_walk(const Node& n, uint64_t addr, Data* d) const {
+  void list_chunks(const Node& n, uint64_t addr, std::vector<H5ChunkRec>* out) const {
+    check(addr, 24);
+    if (std::memcmp(&buf_[addr], "TREE", 4) != 0) throw std::runtime_error("HDF5: bad chunk B-tree");
+    const int level = u8(addr + 5), nent = u16(addr + 6);
+    const size_t nd = n.shape.size();
+    const uint64_t keysz = 8 + 8 * (nd + 1);
+    uint64_t p = addr + 24;
+    for (int i = 0; i < nent; i++, p += keysz + 8) {
+      const uint64_t child = u64(p + keysz);
+      if (level > 0) { list_chunks(n, child, out); continue; }
+      H5ChunkRec r;
+      r.size = u32(p); r.mask = u32(p + 4); r.addr = child;
+      for (size_t k = 0; k < nd; k++) r.offs.push_back(u64(p + 8 + 8 * k));
+      out->push_back(r);
+    }
+  }
+
+  // decodes the chunks that overlap rows [g0, g0+rows) of the first dimension into d (whose first row is g0)
+  void chunk_walk(const Node& n, uint64_t addr, Data* d, uint64_t g0, uint64_t rows) const {
+    check(addr, 24);
     if (std::memcmp(&buf_[addr], "TREE", 4) != 0) throw std::runtime_error("HDF5: bad chunk B-tree");
     const int level = u8(addr + 5), nent = u16(addr + 6);
     const size_t nd = n.shape.size();
@@ -187,11 +271,19 @@ class H5Reader {
     for (int i = 0; i < nent; i++, p += keysz + 8) {
       const uint32_t csize = u32(p), mask = u32(p + 4);
       const uint64_t child = u64(p + keysz);
-      if (level > 0) { chunk_walk(n, child, d); continue; }
+      if (level > 0) {
+        // children are ordered by their first key: skip those that end before g0 or start beyond the range
+        const uint64_t first = u64(p + 8), next = u64(p + keysz + 8 + 8);
+        if (first >= g0 + rows) break;
+        if (i + 1 < nent && next + n.cdims[0] <= g0) continue;   // every chunk of this child ends before row g0
+        chunk_walk(n, child, d, g0, rows);
+        continue;
+      }
       std::vector<uint64_t> offs(nd);
       for (size_t k = 0; k < nd; k++) offs[k] = u64(p + 8 + 8 * k);
+      if (offs[0] >= g0 + rows || offs[0] + n.cdims[0] <= g0) continue;
       check(child, csize);
-      std::vector<char> raw(buf_.begin() + child, buf_.begin() + child + csize);
+      std::vector<char> raw(buf_.data() + child, buf_.data() + child + csize);
       size_t nelem = 1;
       for (auto c : n.cdims) nelem *= c;
       for (int fi = (int)n.filters.size() - 1; fi >= 0; fi--) {
@@ -219,9 +311,15 @@ class H5Reader {
         bool inside = true;
         uint64_t lin = 0;
         for (size_t k = 0; k < nd; k++) {
-          const uint64_t g = offs[k] + idx[k];
+          uint64_t g = offs[k] + idx[k];
           if (g >= n.shape[k]) { inside = false; break; }
-          lin = lin * n.shape[k] + g;
+          if (k == 0) {
+            if (g < g0 || g >= g0 + rows) { inside = false; break; }
+            g -= g0;
+            lin = g;
+          } else {
+            lin = lin * n.shape[k] + g;
+          }
         }
         if (inside) d->v[lin] = elem(n, raw.data() + e * n.dt_size);
         for (int k = (int)nd - 1; k >= 0; k--) { if (++idx[k] < n.cdims[k]) break; idx[k] = 0; }
@@ -229,18 +327,23 @@ class H5Reader {
     }
   }
 
-  Data read_dataset(const Node& n) const {
+  Data read_dataset(const Node& n, uint64_t g0, uint64_t rows) const {
     Data d;
     d.shape = n.shape;
-    size_t total = 1;
-    for (auto s : n.shape) total *= s;
-    d.v.assign(total, 0.0);
+    if (n.shape.empty()) throw std::runtime_error("HDF5: scalar dataspace not supported");
+    if (rows == UNDEF) { g0 = 0; rows = n.shape[0]; }
+    if (g0 + rows > n.shape[0]) throw std::runtime_error("HDF5: rows out of range");
+    d.shape[0] = rows;
+    size_t rowsz = 1;
+    for (size_t k = 1; k < n.shape.size(); k++) rowsz *= n.shape[k];
+    const size_t total = rows * rowsz;
+    d.v.assign(total, n.has_fill ? n.fill : 0.0);   // never-written chunks read as the fill value
     if (n.addr == UNDEF) return d;
     if (n.layout == 1) {
-      check(n.addr, total * n.dt_size);
-      for (size_t i = 0; i < total; i++) d.v[i] = elem(n, &buf_[n.addr + i * n.dt_size]);
+      check(n.addr + g0 * rowsz * n.dt_size, total * n.dt_size);
+      for (size_t i = 0; i < total; i++) d.v[i] = elem(n, &buf_[n.addr + (g0 * rowsz + i) * n.dt_size]);
     } else if (n.layout == 2) {
-      chunk_walk(n, n.addr, &d);
+      chunk_walk(n, n.addr, &d, g0, rows);
     } else {
       throw std::runtime_error("HDF5 layout not supported");
     }

@@ -5,19 +5,24 @@
 //     jobs_prepare            -> read the parameter file (namelists) and the input file
 //     jobs_reads_galaxy_list  -> optional 1-based galaxy ids on the command line (single-galaxy mode)
 //     jobs_distribute(dynamo_run, write_output, ...)  (source/distributor.f90:180)
-//                             -> mag_solve_partitioned: static + work-stealing chunks over the GPUs
+//                             -> checkpoint cycles of p_ncheckpoint galaxies (:253-337), each solved by
+//                                mag_partition_solve (static + work-stealing chunks over the GPUs) and
+//                                followed by a flush of the output file; STOP file / p_max_walltime end
+//                                the run gracefully after a cycle (:299-312)
 //     write_output            -> unit conversion table of source/output.f90:63-201, Log/* datasets
 // The reference cannot be built in this image (no Fortran/MPI/HDF5/GSL toolchain), so the
 // host side above the C ABI is C++; INTEGRATION.md shows the ISO_C_BINDING shim that lets the
 // unchanged Fortran driver call the same entry points.
 //
-// Input: the reference's HDF5 input file (own minimal reader).  Output: the reference's
-// dataset names and shapes (Output/<q> [ngal][nx][nz], scalars [ngal][nz], Log/status ...),
-// written either as an HDF5 file in the reference's layout (mag_hdf5_writer.hpp: /Output, /Log,
-// units/description attributes, the namelists as root attributes; the default) or, when the
-// output name ends in .npz, as an uncompressed .npz container (readable with numpy.load).
+// Input: the reference's HDF5 input file (own minimal reader), or --raw-input <file> (a flat binary
+// catalogue, tools/make_raw_catalogue.py: the synthetic catalogues of BASELINE configs 3-5).
+// Output: the reference's HDF5 layout (mag_hdf5_writer.hpp): every dataset has one row per galaxy of
+// the INPUT FILE -- also in single-galaxy mode --, chunked + deflate, fill value -1d50 where nothing
+// was written; the file is the checkpoint: an existing one is extended, galaxies whose Log/completed
+// flag is set are skipped (IO_start_galaxy, IO_hdf5.f90:244-266).
 //
-//   Magnetizer_b200 <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.npz]
+//   Magnetizer_b200 <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.hdf5]
+//                   [--restart] [--stop-after N] [--dry-run] [--raw-input file]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -29,7 +34,6 @@
 #include <vector>
 
 #include <cuda_runtime.h>
-#include <zlib.h>
 
 #include "../../include/magnetizer_b200.h"
 #include "mag_hdf5_reader.hpp"
@@ -76,88 +80,6 @@ maghost::Hdf5Writer::TextAttrs quantity_attrs(const std::string& q) {
   return a;
 }
 
-// One output sink for both containers: HDF5 (reference layout) or .npz
-struct OutputFile {
-  std::unique_ptr<maghost::Hdf5Writer> h5;
-  std::unique_ptr<struct NpzWriter> npz;
-  void add_f64(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const double* data);
-  void add_status(const std::vector<size_t>& shape, const char* data);
-  void add_i32(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const int32_t* data);
-  void close();
-};
-
-// ---- uncompressed .npz (zip of .npy files, "stored" method)
-struct NpzWriter {
-  FILE* f;
-  struct Entry { std::string name; uint32_t crc, size, offset; };
-  std::vector<Entry> entries;
-  explicit NpzWriter(const std::string& path) : f(std::fopen(path.c_str(), "wb")) {}
-  bool ok() const { return f != nullptr; }
-  static void le16(std::string& s, uint16_t v) { s.push_back((char)(v & 255)); s.push_back((char)(v >> 8)); }
-  static void le32(std::string& s, uint32_t v) { for (int i = 0; i < 4; i++) s.push_back((char)((v >> (8 * i)) & 255)); }
-  void add(const std::string& key, const char* descr, const std::vector<size_t>& shape, const void* data, size_t nbytes) {
-    std::string hdr = std::string("{'descr': '") + descr + "', 'fortran_order': False, 'shape': (";
-    for (size_t i = 0; i < shape.size(); i++) hdr += std::to_string(shape[i]) + (shape.size() == 1 || i + 1 < shape.size() ? "," : "");
-    hdr += "), }";
-    while ((10 + hdr.size() + 1) % 64 != 0) hdr.push_back(' ');
-    hdr.push_back('\n');
-    std::string npy("\x93NUMPY\x01\x00", 8);
-    le16(npy, (uint16_t)hdr.size());
-    npy += hdr;
-    const std::string name = key + ".npy";
-    uint32_t crc = crc32(0L, (const Bytef*)npy.data(), (uInt)npy.size());
-    crc = crc32(crc, (const Bytef*)data, (uInt)nbytes);
-    const uint32_t size = (uint32_t)(npy.size() + nbytes);
-    Entry e{name, crc, size, (uint32_t)std::ftell(f)};
-    std::string lh;
-    le32(lh, 0x04034b50); le16(lh, 20); le16(lh, 0); le16(lh, 0); le16(lh, 0); le16(lh, 0x21);
-    le32(lh, crc); le32(lh, size); le32(lh, size); le16(lh, (uint16_t)name.size()); le16(lh, 0);
-    lh += name;
-    std::fwrite(lh.data(), 1, lh.size(), f);
-    std::fwrite(npy.data(), 1, npy.size(), f);
-    std::fwrite(data, 1, nbytes, f);
-    entries.push_back(e);
-  }
-  void close() {
-    const uint32_t cd_off = (uint32_t)std::ftell(f);
-    std::string cd;
-    for (const auto& e : entries) {
-      le32(cd, 0x02014b50); le16(cd, 20); le16(cd, 20); le16(cd, 0); le16(cd, 0); le16(cd, 0); le16(cd, 0x21);
-      le32(cd, e.crc); le32(cd, e.size); le32(cd, e.size); le16(cd, (uint16_t)e.name.size()); le16(cd, 0); le16(cd, 0);
-      le16(cd, 0); le16(cd, 0); le32(cd, 0); le32(cd, e.offset);
-      cd += e.name;
-    }
-    std::string end;
-    le32(end, 0x06054b50); le16(end, 0); le16(end, 0); le16(end, (uint16_t)entries.size()); le16(end, (uint16_t)entries.size());
-    le32(end, (uint32_t)cd.size()); le32(end, cd_off); le16(end, 0);
-    std::fwrite(cd.data(), 1, cd.size(), f);
-    std::fwrite(end.data(), 1, end.size(), f);
-    std::fclose(f);
-    f = nullptr;
-  }
-};
-
-void OutputFile::add_f64(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const double* data) {
-  size_t n = 1;
-  for (size_t d : shape) n *= d;
-  if (h5) h5->add_dataset(group, name, maghost::Hdf5Writer::F64, std::vector<uint64_t>(shape.begin(), shape.end()), data, quantity_attrs(name));
-  else npz->add(group + "/" + name, "<f8", shape, data, n * 8);
-}
-void OutputFile::add_status(const std::vector<size_t>& shape, const char* data) {
-  if (h5) h5->add_dataset("Log", "status", maghost::Hdf5Writer::CHAR1, std::vector<uint64_t>(shape.begin(), shape.end()), data, quantity_attrs("status"));
-  else npz->add("Log/status", "|S1", shape, data, shape[0] * shape[1]);
-}
-void OutputFile::add_i32(const std::string& group, const std::string& name, const std::vector<size_t>& shape, const int32_t* data) {
-  size_t n = 1;
-  for (size_t d : shape) n *= d;
-  if (h5) h5->add_dataset(group, name, maghost::Hdf5Writer::I32, std::vector<uint64_t>(shape.begin(), shape.end()), data);
-  else npz->add(group + "/" + name, "<i4", shape, data, n * 4);
-}
-void OutputFile::close() {
-  if (h5) h5->close();
-  if (npz) npz->close();
-}
-
 // the namelists as gfortran prints them into one record (IO_hdf5.f90:191-216; parsed by
 // python/magnetizer/parameters.py): "&NAME  KEY=value, KEY=value, /"
 std::string nml_text(const char* name, const std::vector<std::pair<std::string, std::string>>& kv) {
@@ -182,7 +104,9 @@ void write_parameter_attributes(maghost::Hdf5Writer& w, const maghost::RunConfig
       {"p_no_magnetic_fields_test_run", fbool(p.p_no_magnetic_fields_test_run)}, {"p_MAX_FAILS", fint(p.p_MAX_FAILS)},
       {"p_random_seed", fint(p.p_random_seed)}}));
   w.add_root_attribute("io_parameters", nml_text("IO_PARAMETERS", {{"output_file_name", "\"" + cfg.output_file_name + "\""},
-      {"input_file_name", "\"" + cfg.input_file_name + "\""}, {"p_IO_separate_output", "T"}, {"p_IO_chunking", "F"}, {"p_IO_compression", "F"}}));
+      {"input_file_name", "\"" + cfg.input_file_name + "\""}, {"p_IO_separate_output", "T"}, {"p_IO_chunking", fbool(cfg.p_IO_chunking)},
+      {"p_IO_number_of_galaxies_in_chunks", fint(cfg.p_IO_number_of_galaxies_in_chunks)}, {"p_IO_compression", fbool(cfg.p_IO_compression)},
+      {"p_IO_compression_level", fint(cfg.p_IO_compression_level)}, {"p_ncheckpoint", fint(cfg.p_ncheckpoint)}}));
   w.add_root_attribute("grid_parameters", nml_text("GRID_PARAMETERS", {{"p_nx_ref", fint(p.p_nx_ref)}, {"p_nx_MAX", fint(p.p_nx_MAX)},
       {"p_rmax_over_rdisk", fnum(p.p_rmax_over_rdisk)}}));
   w.add_root_attribute("dynamo_parameters", nml_text("DYNAMO_PARAMETERS", {{"Dyn_quench", fbool(p.Dyn_quench)}, {"Alg_quench", fbool(p.Alg_quench)},
@@ -203,23 +127,71 @@ void write_parameter_attributes(maghost::Hdf5Writer& w, const maghost::RunConfig
       {"rmin_over_rmax", fnum(p.rmin_over_rmax)}, {"p_ignore_satellite_DM_haloes", fbool(p.p_ignore_satellite_DM_haloes)},
       {"p_enable_P2", fbool(p.p_enable_P2)}, {"p_minimum_density", fnum(p.p_minimum_density)}, {"p_use_Pdm", fbool(p.p_use_Pdm)},
       {"p_use_Pbulge", fbool(p.p_use_Pbulge)}, {"p_halo_contraction", fbool(p.p_halo_contraction)}}));
-  w.add_root_attribute("outflow_parameters", nml_text("OUTFLOW_PARAMETERS", {{"p_outflow_type", "\"no_outflow\""}}));
+  static const char* const kOutflow[] = {"no_outflow", "vturb", "wind", "superbubble_simple", "superbubble"};
+  w.add_root_attribute("outflow_parameters", nml_text("OUTFLOW_PARAMETERS", {
+      {"p_outflow_type", std::string("\"") + kOutflow[p.outflow_type >= 0 && p.outflow_type < 5 ? p.outflow_type : 0] + "\""},
+      {"p_outflow_Lsn", fnum(p.p_outflow_Lsn)}, {"p_outflow_fOB", fnum(p.p_outflow_fOB)}, {"p_outflow_etaSN", fnum(p.p_outflow_etaSN)},
+      {"p_tOB", fnum(p.p_tOB)}, {"p_N_SN1OB", fnum(p.p_N_SN1OB)}, {"p_outflow_hot_gas_density", fnum(p.p_outflow_hot_gas_density)},
+      {"p_outflow_nu0", fnum(p.p_outflow_nu0)}, {"p_outflow_alphahot", fnum(p.p_outflow_alphahot)}, {"p_outflow_Vhot", fnum(p.p_outflow_Vhot)}}));
   w.add_root_attribute("File creation", "magnetizer_b200 host driver");
+}
+
+}  // namespace
+
+
+namespace {
+
+// flat binary catalogue (tools/make_raw_catalogue.py): "MAGRAW1\0", int64 ngal, int64 nz, t[nz], inputs[13][ngal][nz]
+maghost::MagnetizerInput load_raw_input(const std::string& path) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot open " + path);
+  char magic[8];
+  int64_t dims[2];
+  maghost::MagnetizerInput in;
+  bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "MAGRAW1", 8) == 0 && std::fread(dims, 8, 2, f) == 2;
+  if (ok) {
+    in.ngal = (int)dims[0]; in.nz = (int)dims[1];
+    in.t_gyr.resize(in.nz);
+    in.inputs.resize((size_t)13 * in.ngal * in.nz);
+    ok = std::fread(in.t_gyr.data(), 8, in.nz, f) == (size_t)in.nz && std::fread(in.inputs.data(), 8, in.inputs.size(), f) == in.inputs.size();
+  }
+  std::fclose(f);
+  if (!ok) throw std::runtime_error(path + ": not a raw catalogue");
+  return in;
+}
+
+struct HostBuf {   // page-locked host memory every GPU can store into (mag_host_alloc)
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) mag_host_free(p);
+    p = mag_host_alloc(n);
+    bytes = p ? n : 0;
+    if (!p) throw std::runtime_error("cannot allocate page-locked host memory");
+  }
+  ~HostBuf() { if (p) mag_host_free(p); }
+};
+
+double seconds_since(const std::chrono::steady_clock::time_point& t0) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // namespace
 
 int main(int argc, char** argv) {
   if (argc < 2) {
-    std::fprintf(stderr, "usage: %s <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.hdf5|file.npz]\n"
-                         "          [--restart] [--stop-after N] [--dry-run]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.hdf5]\n"
+                         "          [--restart] [--stop-after N] [--dry-run] [--raw-input file]\n", argv[0]);
     return 2;
   }
   try {
+    const auto t_start = std::chrono::steady_clock::now();
     maghost::RunConfig cfg = maghost::load_run_config(argv[1]);
+    for (const auto& wmsg : cfg.warnings) std::fprintf(stderr, "warning: %s\n", wmsg.c_str());
     std::vector<int32_t> list, devices;
-    int chunk = 2048;
-    std::string out_path;
+    int chunk = 0;
+    std::string out_path, raw_input;
     bool dry_run = false, restart = false;
     long stop_after = -1;
     for (int i = 2; i < argc; i++) {
@@ -227,22 +199,22 @@ int main(int argc, char** argv) {
       if (a == "--dry-run") { dry_run = true; continue; }
       if (a == "--restart") { restart = true; continue; }
       if (a == "--stop-after" && i + 1 < argc) { stop_after = std::atol(argv[++i]); continue; }
+      if (a == "--raw-input" && i + 1 < argc) { raw_input = argv[++i]; continue; }
       if (a == "--devices" && i + 1 < argc) {
         for (char* tok = std::strtok(argv[++i], ","); tok; tok = std::strtok(nullptr, ",")) devices.push_back(std::atoi(tok));
       } else if (a == "--chunk" && i + 1 < argc) chunk = std::atoi(argv[++i]);
       else if (a == "--out" && i + 1 < argc) out_path = argv[++i];
       else list.push_back(std::atoi(a.c_str()));
     }
-    if (cfg.input_file_name.empty()) throw std::runtime_error("input_file_name missing in io_parameters");
-    const maghost::MagnetizerInput in = maghost::load_magnetizer_input(cfg.input_file_name);
-    // jobs_reads_galaxy_list: ids are 1-based rows of the input file
-    if (list.empty()) for (int g = 1; g <= in.ngal; g++) list.push_back(g);
-    for (int g : list) if (g < 1 || g > in.ngal) throw std::runtime_error("galaxy id out of range: " + std::to_string(g));
-    const int ngal = (int)list.size(), nz = in.nz, nr = cfg.params.p_nx_ref;
-    std::vector<double> inputs((size_t)13 * ngal * nz);
-    for (int c = 0; c < 13; c++)
-      for (int k = 0; k < ngal; k++)
-        std::memcpy(&inputs[((size_t)c * ngal + k) * nz], &in.inputs[((size_t)c * in.ngal + (list[k] - 1)) * nz], sizeof(double) * nz);
+    const maghost::MagnetizerInput in = raw_input.empty() ? maghost::load_magnetizer_input(cfg.input_file_name) : load_raw_input(raw_input);
+    // jobs_reads_galaxy_list: ids are 1-based rows of the input file; the output has one row per galaxy of the FILE
+    const int ngals = in.ngal, nz = in.nz, nr = cfg.params.p_nx_ref;
+    if (list.empty()) for (int g = 1; g <= ngals; g++) list.push_back(g);
+    std::vector<char> selected(ngals, 0);
+    for (int g : list) {
+      if (g < 1 || g > ngals) throw std::runtime_error("galaxy id out of range: " + std::to_string(g));
+      selected[g - 1] = 1;
+    }
     // requested quantities (output_quantities_list; default: everything)
     std::vector<int32_t> pq, sq;
     std::vector<std::string> names = cfg.output_quantities_list;
@@ -257,34 +229,36 @@ int main(int argc, char** argv) {
     if (!have_rkpc) pq.push_back(MAG_Q_RKPC);  // Output/r is always written (output.f90:56-60)
     // ---- resume: the output file doubles as checkpoint (distributor.f90:150-156).  Galaxies whose
     // Log/completed flag is set are not solved again (IO_start_galaxy, IO_hdf5.f90:244-266);
-    // --restart ignores an existing file, --stop-after N ends this invocation after N galaxies
-    // (the graceful stop of the STOP file / p_max_walltime, distributor.f90:299-312).
-    if (out_path.empty()) out_path = cfg.output_file_name.empty() ? "magnetizer_b200_output.hdf5" : cfg.output_file_name;
-    const bool as_npz = out_path.size() > 4 && out_path.compare(out_path.size() - 4, 4, ".npz") == 0;
+    // --restart ignores an existing file, --stop-after N ends this invocation after N galaxies.
+    if (out_path.empty()) out_path = cfg.output_file_name;
     std::unique_ptr<maghost::H5Reader> prev;
-    std::vector<char> completed(ngal, 0);
-    if (!restart && !as_npz) {
-      if (FILE* t = std::fopen(out_path.c_str(), "rb")) {
-        std::fclose(t);
+    std::vector<char> completed(ngals, 0);
+    if (!restart) {
+      if (FILE* tf = std::fopen(out_path.c_str(), "rb")) {
+        std::fclose(tf);
         prev.reset(new maghost::H5Reader(out_path));
-        const maghost::H5Reader::Data ids = prev->read("Log/gal_id"), comp = prev->read("Log/completed");
-        bool same = ids.v.size() == (size_t)ngal && comp.v.size() == (size_t)ngal;
-        for (int g = 0; same && g < ngal; g++) same = (int32_t)ids.v[g] == list[g];
-        if (!same) throw std::runtime_error("cannot resume: " + out_path + " holds another galaxy list (use --restart)");
-        for (int g = 0; g < ngal; g++) completed[g] = comp.v[g] > 0.5;
+        const std::vector<uint64_t> shp = prev->exists("Output/r") ? prev->shape("Output/r") : std::vector<uint64_t>();
+        if (shp != std::vector<uint64_t>{(uint64_t)ngals, (uint64_t)nr, (uint64_t)nz})
+          throw std::runtime_error("cannot resume: " + out_path + " was written for another input file or grid (use --restart)");
+        const maghost::H5Reader::Data comp = prev->read("Log/completed");
+        for (int g = 0; g < ngals; g++) completed[g] = comp.v[g] > 0.5;   // never-written rows hold the fill value
       }
     }
     std::vector<int> todo;
-    for (int g = 0; g < ngal; g++) if (!completed[g]) todo.push_back(g);
+    size_t n_done_before = 0;
+    for (int g = 0; g < ngals; g++) {
+      if (!selected[g]) continue;
+      if (completed[g]) n_done_before++; else todo.push_back(g);
+    }
     const size_t n_open = todo.size();
     if (stop_after >= 0 && todo.size() > (size_t)stop_after) todo.resize((size_t)stop_after);
-    if (dry_run) std::printf("resume %s: %zu of %d galaxies completed, %zu to solve now\n", prev ? "yes" : "no", ngal - n_open, ngal, todo.size());
     if (dry_run) {  // host-side logic only (parameter file, input file, galaxy list, quantity list): no device needed
-      std::printf("dry-run ngal %d nz %d list %zu p_courant_v %.17g p_nx_ref %d p_random_seed %d\n", in.ngal, nz, list.size(),
+      std::printf("resume %s: %zu of %zu galaxies completed, %zu to solve now\n", prev ? "yes" : "no", n_done_before, list.size(), todo.size());
+      std::printf("dry-run ngal %d nz %d list %zu p_courant_v %.17g p_nx_ref %d p_random_seed %d\n", ngals, nz, list.size(),
                   cfg.params.p_courant_v, cfg.params.p_nx_ref, cfg.params.p_random_seed);
       for (int c = 0; c < 13; c++) {
         double sum = 0;
-        for (size_t k = 0; k < (size_t)ngal * nz; k++) sum += inputs[(size_t)c * ngal * nz + k];
+        for (int g = 0; g < ngals; g++) if (selected[g]) for (int iz = 0; iz < nz; iz++) sum += in.inputs[((size_t)c * ngals + g) * nz + iz];
         std::printf("column %s sum %.17g\n", maghost::kInputColumns[c], sum);
       }
       std::printf("t %.17g .. %.17g\nprofiles", in.t_gyr.front(), in.t_gyr.back());
@@ -299,103 +273,177 @@ int main(int argc, char** argv) {
       if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) throw std::runtime_error("no CUDA device (there is no CPU fallback)");
       for (int d = 0; d < nd; d++) devices.push_back(d);
     }
-    const int nsel = (int)todo.size();
-    std::vector<int32_t> sel_ids(nsel);
-    std::vector<double> sel_inputs((size_t)13 * nsel * nz);
-    for (int k = 0; k < nsel; k++) sel_ids[k] = list[todo[k]];
-    for (int c = 0; c < 13; c++)
-      for (int k = 0; k < nsel; k++)
-        std::memcpy(&sel_inputs[((size_t)c * nsel + k) * nz], &inputs[((size_t)c * ngal + todo[k]) * nz], sizeof(double) * nz);
-    std::vector<double> profiles((size_t)pq.size() * nsel * nz * nr), scalars((size_t)sq.size() * nsel * nz);
-    std::vector<char> status((size_t)nsel * nz);
-    std::vector<int32_t> nsteps(nsel), error(nsel), done(devices.size()), stolen(devices.size());
-    std::vector<int64_t> stages(nsel);
-    std::vector<uint32_t> flags(nsel);
-    mag_outputs_t out{profiles.data(), scalars.empty() ? nullptr : scalars.data(), status.data(), nsteps.data(), error.data(),
-                      stages.data(), flags.data()};
-    std::printf("Magnetizer (B200 path): '%s'  %d galaxies x %d snapshots (%zu already completed, %d to solve), %zu GPU(s), chunk %d\n",
-                cfg.model_name.c_str(), ngal, nz, ngal - n_open, nsel, devices.size(), chunk);
-    const auto t0 = std::chrono::steady_clock::now();
-    if (nsel > 0) {
-      const int rc = mag_solve_partitioned(&cfg.params, (int)devices.size(), devices.data(), nsel, sel_ids.data(), nz, in.t_gyr.data(),
-                                           sel_inputs.data(), (int)pq.size(), pq.data(), (int)sq.size(), sq.data(), &out, chunk,
-                                           done.data(), stolen.data());
-      if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
+    mag_partition_t* part = nullptr;
+    if (mag_partition_create(&cfg.params, (int)devices.size(), devices.data(), &part) != MAG_OK)
+      throw std::runtime_error(std::string("cannot create the solver: ") + mag_partition_last_error());
+
+    // ---- the output file (IO_start, IO_hdf5.f90:114-241): new, or the existing one extended in place
+    maghost::Hdf5Writer::Options wopt;
+    wopt.chunking = cfg.p_IO_chunking != 0; wopt.gals_per_chunk = cfg.p_IO_number_of_galaxies_in_chunks;
+    wopt.compression = cfg.p_IO_compression != 0; wopt.level = cfg.p_IO_compression_level;
+    maghost::Hdf5Writer w(out_path, wopt, /*extend=*/prev != nullptr);
+    w.add_group("Output");
+    w.add_group("Log");
+    write_parameter_attributes(w, cfg);
+    struct Col { std::string path; int h; };
+    std::vector<Col> prof_cols, scal_cols;
+    int h_r = -1;
+    const std::vector<uint64_t> d3{(uint64_t)ngals, (uint64_t)nr, (uint64_t)nz}, d2{(uint64_t)ngals, (uint64_t)nz}, d1{(uint64_t)ngals, 1};
+    for (int q : pq) {
+      const std::string name = kProfileNames[q];
+      if (name != "rkpc" || have_rkpc) prof_cols.push_back({"Output/" + name, w.create_dataset("Output", name, maghost::Hdf5Writer::F64, d3, quantity_attrs(name))});
+      else prof_cols.push_back({"", -1});
+      if (name == "rkpc") h_r = w.create_dataset("Output", "r", maghost::Hdf5Writer::F64, d3, quantity_attrs("r"));
     }
-    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    // ---- write_output (output.f90:23-236): unit conversion, [ngal][nx][nz] layout, Log group.
-    // Galaxies completed by an earlier invocation keep their rows, galaxies not solved yet hold
-    // "never written" markers and completed = 0.
-    const std::string tmp_path = out_path + ".tmp";
-    OutputFile w;
-    if (as_npz) {
-      w.npz.reset(new NpzWriter(tmp_path));
-      if (!w.npz->ok()) throw std::runtime_error("cannot write " + tmp_path);
-    } else {
-      w.h5.reset(new maghost::Hdf5Writer(tmp_path));
-      w.h5->add_group("Output");
-      w.h5->add_group("Log");
-      write_parameter_attributes(*w.h5, cfg);
-    }
-    auto previous = [&](const std::string& path, size_t n) {   // dataset of the resumed file or "never written"
-      if (!prev) return std::vector<double>(n, MAG_INVALID);
-      maghost::H5Reader::Data d = prev->read(path);
-      if (d.v.size() != n) throw std::runtime_error("cannot resume: " + path + " has another shape (use --restart)");
-      return d.v;
-    };
-    long long total_stages = 0;
-    for (auto s : stages) total_stages += s;
-    for (size_t q = 0; q < pq.size(); q++) {
-      const std::string name = kProfileNames[pq[q]];
-      const double fac = unit_factor(name);
-      const double* src = &profiles[q * (size_t)nsel * nz * nr];
-      std::vector<double> full = previous("Output/" + std::string(name == "rkpc" && !have_rkpc ? "r" : name), (size_t)ngal * nr * nz);
-      for (int k = 0; k < nsel; k++)
-        for (int iz = 0; iz < nz; iz++)
-          for (int i = 0; i < nr; i++) {
-            const double v = src[((size_t)k * nz + iz) * nr + i];
-            full[((size_t)todo[k] * nr + i) * nz + iz] = (v == MAG_INVALID) ? v : v * fac;
-          }
-      if (name != "rkpc" || have_rkpc) w.add_f64("Output", name, {(size_t)ngal, (size_t)nr, (size_t)nz}, full.data());
-      if (name == "rkpc") w.add_f64("Output", "r", {(size_t)ngal, (size_t)nr, (size_t)nz}, full.data());
-    }
-    for (size_t q = 0; q < sq.size(); q++) {
-      std::vector<double> full = previous(std::string("Output/") + kScalarNames[sq[q]], (size_t)ngal * nz);
-      for (int k = 0; k < nsel; k++)
-        std::memcpy(&full[(size_t)todo[k] * nz], &scalars[(q * (size_t)nsel + k) * nz], sizeof(double) * nz);
-      w.add_f64("Output", kScalarNames[sq[q]], {(size_t)ngal, (size_t)nz}, full.data());
-    }
-    std::vector<char> status_full((size_t)ngal * nz, '-');
-    if (prev) {
-      const std::vector<double> st = previous("Log/status", (size_t)ngal * nz);
-      for (size_t i = 0; i < st.size(); i++) status_full[i] = (char)(int)st[i];
-    }
-    for (int k = 0; k < nsel; k++) std::memcpy(&status_full[(size_t)todo[k] * nz], &status[(size_t)k * nz], nz);
-    w.add_status({(size_t)ngal, (size_t)nz}, status_full.data());
-    std::vector<double> log_n = prev ? previous("Log/nsteps", ngal) : std::vector<double>(ngal, 0.0);
-    std::vector<double> log_c = prev ? previous("Log/completed", ngal) : std::vector<double>(ngal, 0.0);
-    std::vector<double> log_rt = prev ? previous("Log/runtime", ngal) : std::vector<double>(ngal, 0.0);
+    for (int q : sq) scal_cols.push_back({std::string("Output/") + kScalarNames[q], w.create_dataset("Output", kScalarNames[q], maghost::Hdf5Writer::F64, d2, quantity_attrs(kScalarNames[q]))});
+    const int h_status = w.create_dataset("Log", "status", maghost::Hdf5Writer::CHAR1, d2, quantity_attrs("status"), false);
+    const int h_nsteps = w.create_dataset("Log", "nsteps", maghost::Hdf5Writer::F64, d1, quantity_attrs("nsteps"));
+    const int h_completed = w.create_dataset("Log", "completed", maghost::Hdf5Writer::F64, d1);
+    const int h_runtime = w.create_dataset("Log", "runtime", maghost::Hdf5Writer::F64, d1, quantity_attrs("runtime"));
+    std::vector<std::pair<std::string, int>> all_sets;
+    for (auto& c : prof_cols) if (c.h >= 0) all_sets.push_back({c.path, c.h});
+    all_sets.push_back({"Output/r", h_r});
+    for (auto& c : scal_cols) all_sets.push_back({c.path, c.h});
+    all_sets.push_back({"Log/status", h_status}); all_sets.push_back({"Log/nsteps", h_nsteps});
+    all_sets.push_back({"Log/completed", h_completed}); all_sets.push_back({"Log/runtime", h_runtime});
+    if (prev)
+      for (auto& kv : all_sets) {
+        if (!prev->exists(kv.first)) continue;   // a quantity the earlier invocation did not ask for
+        w.adopt(kv.second, prev->chunks(kv.first));
+        w.adopt_contiguous(kv.second, prev->contiguous_address(kv.first));
+      }
+    const size_t cs = (size_t)w.gals_per_block(h_r), nblocks = (size_t)w.n_blocks(h_r);
+
+    std::printf("Magnetizer (B200 path): '%s'  %d galaxies x %d snapshots in the input, %zu selected (%zu already completed, %zu to solve), %zu GPU(s)\n",
+                cfg.model_name.c_str(), ngals, nz, list.size(), n_done_before, todo.size(), devices.size());
+    (void)n_open;
+    // ---- checkpoint cycles (distributor.f90:253-337): blocks of galaxies are accumulated until at least
+    // p_ncheckpoint galaxies are to be solved; solve, write, flush; then look for the STOP file / the walltime
+    std::vector<char> is_todo(ngals, 0);
+    for (int g : todo) is_todo[g] = 1;
+    HostBuf b_in, b_prof, b_scal, b_stat, b_nsteps, b_err, b_ps, b_flags;
+    std::vector<int32_t> done((size_t)devices.size()), stolen((size_t)devices.size()), done_tot(devices.size(), 0), stolen_tot(devices.size(), 0);
     std::map<char, long> counts;
-    for (int k = 0; k < nsel; k++) {
-      const int g = todo[k];
-      log_n[g] = nsteps[k];
-      log_c[g] = error[k] ? 0.0 : 1.0;  // Log/completed is only written when runtime > 0 (distributor.f90:363)
-      log_rt[g] = total_stages > 0 ? secs * (double)stages[k] / (double)total_stages : 0.0;
+    double solve_s = 0, write_s = 0;
+    long long total_stages = 0;
+    size_t solved = 0, cycles = 0;
+    bool stopped = false;
+    const size_t ncheck = (size_t)std::max(1, cfg.p_ncheckpoint);
+    for (size_t kb0 = 0; kb0 < nblocks && !stopped;) {
+      std::vector<int> sel;            // catalogue indices to solve in this cycle, ascending
+      size_t kb1 = kb0;
+      while (kb1 < nblocks && sel.size() < ncheck) {
+        for (size_t g = kb1 * cs; g < std::min((kb1 + 1) * cs, (size_t)ngals); g++) if (is_todo[g]) sel.push_back((int)g);
+        kb1++;
+      }
+      if (sel.empty()) { kb0 = kb1; continue; }
+      const int nsel = (int)sel.size();
+      // -- solve the cycle's galaxies: packed inputs in, packed results out (page-locked: the kernels store into them)
+      b_in.ensure(sizeof(double) * 13 * nsel * nz);
+      b_prof.ensure(sizeof(double) * pq.size() * nsel * nz * nr); b_scal.ensure(sizeof(double) * std::max<size_t>(1, sq.size()) * nsel * nz);
+      b_stat.ensure((size_t)nsel * nz); b_nsteps.ensure(4 * (size_t)nsel); b_err.ensure(4 * (size_t)nsel); b_ps.ensure(8 * (size_t)nsel); b_flags.ensure(4 * (size_t)nsel);
+      double* sin = (double*)b_in.p;
+      std::vector<int32_t> sel_ids(nsel);
+      for (int k = 0; k < nsel; k++) sel_ids[k] = sel[k] + 1;
+      for (int c = 0; c < 13; c++)
+        for (int k = 0; k < nsel; k++)
+          std::memcpy(&sin[((size_t)c * nsel + k) * nz], &in.inputs[((size_t)c * ngals + sel[k]) * nz], sizeof(double) * nz);
+      const double* profiles = (const double*)b_prof.p;
+      const double* scalars = (const double*)b_scal.p;
+      const char* status = (const char*)b_stat.p;
+      const int32_t *nsteps = (const int32_t*)b_nsteps.p, *error = (const int32_t*)b_err.p;
+      const int64_t* stages = (const int64_t*)b_ps.p;
+      mag_outputs_t out{(double*)b_prof.p, sq.empty() ? nullptr : (double*)b_scal.p, (char*)b_stat.p, (int32_t*)b_nsteps.p, (int32_t*)b_err.p,
+                        (int64_t*)b_ps.p, (uint32_t*)b_flags.p};
+      const auto t0 = std::chrono::steady_clock::now();
+      const int rc = mag_partition_solve(part, nsel, sel_ids.data(), nz, in.t_gyr.data(), sin, (int)pq.size(), pq.data(), (int)sq.size(), sq.data(),
+                                         &out, chunk, done.data(), stolen.data());
+      if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
+      const double cyc_s = seconds_since(t0);
+      solve_s += cyc_s;
+      long long cyc_stages = 0;
+      for (int k = 0; k < nsel; k++) cyc_stages += stages[k];
+      total_stages += cyc_stages;
+      for (size_t d = 0; d < devices.size(); d++) { done_tot[d] += done[d]; stolen_tot[d] += stolen[d]; }
+      // -- write_output (output.f90:23-236): unit conversion, (ngals, nx, nz) layout, Log group; block by block
+      const auto t1 = std::chrono::steady_clock::now();
+      std::vector<double> blk3(cs * (size_t)nr * nz), blk2(cs * (size_t)nz), blk1(cs);
+      std::vector<char> blkc(cs * (size_t)nz);
+      size_t k_lo = 0;
+      for (size_t kb = kb0; kb < kb1; kb++) {
+        const size_t g0 = kb * cs, nb = std::min(cs, (size_t)ngals - g0);
+        size_t k_hi = k_lo;
+        while (k_hi < (size_t)nsel && (size_t)sel[k_hi] < g0 + nb) k_hi++;
+        if (k_hi == k_lo) continue;                                   // nothing solved in this block: its chunks stay as they are
+        bool merge = false;                                           // rows an earlier invocation completed are kept
+        for (size_t g = g0; g < g0 + nb; g++) if (completed[g]) merge = true;
+        auto base3 = [&](const std::string& path) {
+          if (merge && prev && prev->exists(path)) { const maghost::H5Reader::Data d = prev->read_rows(path, g0, nb); std::copy(d.v.begin(), d.v.end(), blk3.begin()); }
+          else std::fill(blk3.begin(), blk3.begin() + nb * (size_t)nr * nz, maghost::Hdf5Writer::kFill);
+        };
+        auto base2 = [&](const std::string& path, std::vector<double>& b, size_t row) {
+          if (merge && prev && prev->exists(path)) { const maghost::H5Reader::Data d = prev->read_rows(path, g0, nb); std::copy(d.v.begin(), d.v.end(), b.begin()); }
+          else std::fill(b.begin(), b.begin() + nb * row, maghost::Hdf5Writer::kFill);
+        };
+        for (size_t q = 0; q < pq.size(); q++) {
+          const std::string name = kProfileNames[pq[q]];
+          const double fac = unit_factor(name);
+          const double* src = profiles + q * (size_t)nsel * nz * nr;
+          base3(name == "rkpc" && !have_rkpc ? "Output/r" : "Output/" + name);
+          for (size_t k = k_lo; k < k_hi; k++) {
+            double* dst = &blk3[((size_t)sel[k] - g0) * nr * nz];
+            for (int iz = 0; iz < nz; iz++)
+              for (int i = 0; i < nr; i++) {
+                const double v = src[(k * nz + iz) * nr + i];
+                dst[(size_t)i * nz + iz] = (v == MAG_INVALID) ? v : v * fac;
+              }
+          }
+          if (prof_cols[q].h >= 0) w.write_block(prof_cols[q].h, kb, blk3.data());
+          if (name == "rkpc") w.write_block(h_r, kb, blk3.data());
+        }
+        for (size_t q = 0; q < sq.size(); q++) {
+          base2(scal_cols[q].path, blk2, nz);
+          for (size_t k = k_lo; k < k_hi; k++)
+            std::memcpy(&blk2[((size_t)sel[k] - g0) * nz], &scalars[(q * (size_t)nsel + k) * nz], sizeof(double) * nz);
+          w.write_block(scal_cols[q].h, kb, blk2.data());
+        }
+        if (merge && prev) { const maghost::H5Reader::Data d = prev->read_rows("Log/status", g0, nb); for (size_t i = 0; i < nb * (size_t)nz; i++) blkc[i] = (char)(int)d.v[i]; }
+        else std::fill(blkc.begin(), blkc.begin() + nb * (size_t)nz, '\0');
+        for (size_t k = k_lo; k < k_hi; k++) {
+          std::memcpy(&blkc[((size_t)sel[k] - g0) * nz], &status[k * (size_t)nz], nz);
+          for (int iz = 0; iz < nz; iz++) counts[status[k * (size_t)nz + iz]]++;
+        }
+        w.write_block(h_status, kb, blkc.data());
+        // Log datasets are (ngals, 1) in the reference's file (Fortran (1, ngals), output.f90:37-54)
+        base2("Log/nsteps", blk1, 1);
+        for (size_t k = k_lo; k < k_hi; k++) blk1[(size_t)sel[k] - g0] = nsteps[k];
+        w.write_block(h_nsteps, kb, blk1.data());
+        base2("Log/completed", blk1, 1);
+        for (size_t k = k_lo; k < k_hi; k++) blk1[(size_t)sel[k] - g0] = error[k] ? 0.0 : 1.0;  // only written when runtime > 0 (distributor.f90:363)
+        w.write_block(h_completed, kb, blk1.data());
+        base2("Log/runtime", blk1, 1);
+        for (size_t k = k_lo; k < k_hi; k++) blk1[(size_t)sel[k] - g0] = cyc_stages > 0 ? cyc_s * (double)stages[k] / (double)cyc_stages : 0.0;
+        w.write_block(h_runtime, kb, blk1.data());
+        k_lo = k_hi;
+      }
+      w.flush();                                                      // IO_flush every checkpoint cycle (distributor.f90:336)
+      write_s += seconds_since(t1);
+      solved += (size_t)nsel;
+      cycles++;
+      if (cfg.info > 1) std::printf("  cycle %zu: %d galaxies solved in %.3f s, flushed (%zu of %zu done)\n", cycles, nsel, cyc_s, solved, todo.size());
+      kb0 = kb1;
+      // graceful stop (distributor.f90:299-312): a file named STOP in the working directory, or the walltime
+      if (FILE* sf = std::fopen("STOP", "rb")) { std::fclose(sf); stopped = true; std::printf("  STOP file found: exiting after this cycle\n"); }
+      if (cfg.p_max_walltime > 0 && seconds_since(t_start) > cfg.p_max_walltime) { stopped = true; std::printf("  p_max_walltime reached: exiting after this cycle\n"); }
     }
-    for (char c : status_full) counts[c]++;
-    // Log datasets are (ngals, 1) in the reference's file (Fortran (1, ngals), output.f90:37-54)
-    const std::vector<size_t> log_shape = as_npz ? std::vector<size_t>{(size_t)ngal} : std::vector<size_t>{(size_t)ngal, 1};
-    w.add_f64("Log", "nsteps", log_shape, log_n.data());
-    w.add_f64("Log", "completed", log_shape, log_c.data());
-    w.add_f64("Log", "runtime", log_shape, log_rt.data());
-    w.add_i32("Log", "gal_id", {(size_t)ngal}, list.data());
-    if (as_npz) w.add_f64("Input", "t", {(size_t)nz}, in.t_gyr.data());
     w.close();
     prev.reset();
-    if (std::rename(tmp_path.c_str(), out_path.c_str()) != 0) throw std::runtime_error("cannot rename " + tmp_path + " to " + out_path);
-    std::printf("  solved in %.3f s  (%.1f galaxies/s, %.3e point-stages/s)\n", secs, nsel / secs, total_stages / secs);
+    mag_partition_destroy(part);
+    std::printf("  solved %zu galaxies in %.3f s  (%.1f galaxies/s, %.3e point-stages/s); output written in %.3f s (%.1f MB, %zu flush(es))\n",
+                solved, solve_s, solve_s > 0 ? solved / solve_s : 0.0, solve_s > 0 ? total_stages / solve_s : 0.0, write_s,
+                (double)w.bytes_written() / 1e6, cycles);
     for (size_t d = 0; d < devices.size(); d++)
-      std::printf("  GPU %d: %d chunks (%d stolen)\n", devices[d], done[d], stolen[d]);
+      std::printf("  GPU %d: %d chunks (%d stolen)\n", devices[d], done_tot[d], stolen_tot[d]);
     std::printf("  status codes:");
     for (auto& kv : counts) std::printf(" '%c' x%ld", kv.first, kv.second);
     std::printf("\n  wrote %s\n", out_path.c_str());

@@ -24,10 +24,47 @@ def _row_err(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return out
 
 
-def compare(got: dict, want: dict, rtol: float = RTOL, check_cost: bool = True) -> dict:
+MAG_FLAG_RETRY = 4
+
+
+def _mask_failed_runs(got: dict, want: dict):
+    """Galaxies whose time stepping FAILED in the reference's own terms (status 'm' / 'i': check_f_error
+    tripped, dynamo.f90:222-257).  Such a run is a numerical instability that grows out of rounding noise:
+    the step at which it crosses the 1e8 / 1000 thresholds -- and with it the accumulated time, the number of
+    stages, occasionally the snapshot that ends up 'i' -- depends on the last bit of every operation, also
+    between two builds of the reference (profiles/r2_sensitivity.md).  For these galaxies parity is required
+    of everything up to the last snapshot before the first failure, of the failure itself being reported
+    (same flag; first failing snapshot within one of the reference's), and of nothing after it.
+    Returns copies of (got, want) in which the rows from the first failure on are blanked identically."""
+    gs, ws = np.asarray(got["status"]).view("S1"), np.asarray(want["status"]).view("S1")
+    gf, wf = np.asarray(got["flags"]), np.asarray(want["flags"])
+    assert np.array_equal(gf & MAG_FLAG_RETRY, wf & MAG_FLAG_RETRY), ("retry flag", np.argwhere((gf ^ wf) & MAG_FLAG_RETRY)[:5].ravel())
+    g2 = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in got.items()}
+    w2 = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in want.items()}
+    g2["status"], w2["status"] = g2["status"].view("S1"), w2["status"].view("S1")
+    for g in np.argwhere(wf & MAG_FLAG_RETRY).ravel():
+        first = []
+        for st in (gs[g], ws[g]):
+            bad = np.argwhere((st == b"m") | (st == b"i")).ravel()
+            assert bad.size, f"galaxy index {g}: retry flag without an 'm' / 'i' snapshot"
+            first.append(int(bad[0]))
+        assert abs(first[0] - first[1]) <= 1, f"galaxy index {g}: first failing snapshot {first[0]} vs {first[1]}"
+        s0 = min(first)
+        for d in (g2, w2):
+            d["status"][g, s0:] = b"?"
+            d["profiles"][:, g, s0:] = 0.0
+            d["scalars"][:, g, s0:] = 0.0
+            d["nsteps"][g] = 0
+            d["point_stages"][g] = 0
+    return g2, w2
+
+
+def compare(got: dict, want: dict, rtol: float = RTOL, check_cost: bool = True, failed_runs: str = "strict") -> dict:
     """Asserts parity of two result dicts (layouts of the C ABI); returns
-    {quantity: worst row-relative error}."""
+    {quantity: worst row-relative error}.  failed_runs = "relaxed": see _mask_failed_runs."""
     assert got["profile_names"] == want["profile_names"] and got["scalar_names"] == want["scalar_names"]
+    if failed_runs == "relaxed":
+        got, want = _mask_failed_runs(got, want)
     gs, ws = np.asarray(got["status"]).view("S1"), np.asarray(want["status"]).view("S1")
     if not np.array_equal(gs, ws):
         bad = np.argwhere(gs != ws)
@@ -38,7 +75,8 @@ def compare(got: dict, want: dict, rtol: float = RTOL, check_cost: bool = True) 
         assert np.array_equal(got[k], want[k]), (k, np.argwhere(got[k] != want[k])[:5].ravel())
     assert np.array_equal(got["flags"], want["flags"]), ("flags", np.argwhere(got["flags"] != want["flags"])[:5].ravel())
     if check_cost:
-        assert np.array_equal(got["point_stages"], want["point_stages"]), "point_stages"
+        bad = np.argwhere(np.asarray(got["point_stages"]) != np.asarray(want["point_stages"])).ravel()
+        assert bad.size == 0, ("point_stages", bad[:5], np.asarray(got["point_stages"])[bad[:5]], np.asarray(want["point_stages"])[bad[:5]])
     rep = {}
     for qi, name in enumerate(want["profile_names"]):
         a, b = got["profiles"][qi], want["profiles"][qi]

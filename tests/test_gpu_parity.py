@@ -193,6 +193,21 @@ def test_partitioned_solve_matches_single_context(solver, example_input):
     one = solver.run(ids, t, sub, profiles=prof, scalars=scal)
     two = solve_partitioned(ids, t, sub, devices=[0, 0], chunk=4, profiles=prof, scalars=scal)
     assert two["chunks_done"].sum() == 11
+    # which galaxies run on four-warp teams depends on the batch they are solved in; the two evolve
+    # kernels agree to rounding (~1e-13), not bit for bit
+    compare(two, one, rtol=1e-10)
+    # with the split switched off the result is bit-identical however the catalogue is cut
+    os.environ["MAG_HEAVY_MODE"] = "0"
+    try:
+        from magnetizer_b200.solver import DynamoSolver
+        s0 = DynamoSolver(device=0)
+        try:
+            one = s0.run(ids, t, sub, profiles=prof, scalars=scal)
+        finally:
+            s0.close()
+        two = solve_partitioned(ids, t, sub, devices=[0, 0], chunk=4, profiles=prof, scalars=scal)
+    finally:
+        del os.environ["MAG_HEAVY_MODE"]
     for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
         assert np.array_equal(one[k], two[k]), k
     assert np.array_equal(one["status"], two["status"])
@@ -336,8 +351,11 @@ def test_parameter_sweep(oracle, example_input, name, setp):
     finally:
         s.close()
     ora = oracle.solve_batch(p, ids, t, allin, profiles=prof, scalars=scal)
-    rep = compare(gpu, ora)
-    print(name, "worst:", max(rep.values()), "statuses:", sorted(set(ora["status"].tobytes().decode())),
+    # settings that destabilise some discs (no dark-matter pressure, no satellite haloes, large Courant
+    # factors) contain runs that FAIL in the reference's own terms; parity.py explains what parity means there
+    rep = compare(gpu, ora, failed_runs="relaxed")
+    nfail = int(((ora["flags"] & 4) != 0).sum())
+    print(name, "worst:", max(rep.values()), "failed runs:", nfail, "statuses:", sorted(set(ora["status"].tobytes().decode())),
           "heavy", info["heavy_galaxies"], "replays", info["fast_path_replays"])
     if name.startswith("MAX_FAILS"):
         assert (ora["flags"] & 4).any()       # retries really happen
@@ -415,7 +433,7 @@ def test_heavy_light_split_and_launch_modes(oracle, example_input):
             assert 0 < nh < len(ids), nh
         finally:
             s.close()
-    for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
+    for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):   # same split, same kernels: bit-identical
         assert np.array_equal(res["0"][k], res["1"][k]), k
     ora = oracle.solve_batch(oracle.default_params(), ids, t, inputs, profiles=prof, scalars=scal)
     compare(res["1"], ora)
@@ -502,9 +520,7 @@ def test_partition_pinned_in_place_and_resident(example_input):
         out = part.alloc_outputs(len(ids), t.size, prof, scal, pinned=True)
         two = part.solve(ids, t, sub, chunk=8, profiles=prof, scalars=scal, out=out)
         assert two["chunks_done"].sum() == 8
-        for k in ("profiles", "scalars", "nsteps", "error", "point_stages", "flags"):
-            assert np.array_equal(one[k], np.asarray(two[k])), k
-        assert np.array_equal(one["status"], two["status"])
+        compare({k: (np.asarray(v) if isinstance(v, np.ndarray) else v) for k, v in two.items() if not k.startswith("chunks")}, one, rtol=1e-10)
         # resident form: one full copy of the inputs / outputs per listed device
         dev = torch.device("cuda", 0)
         nd, n, nz, nr = 2, len(ids), t.size, part.params.p_nx_ref
@@ -520,7 +536,9 @@ def test_partition_pinned_in_place_and_resident(example_input):
         torch.cuda.synchronize()
         assert st["chunks_done"].sum() == 8 and (owner >= 0).all()
         got = np.stack([d_prof[owner[g]][:, g].cpu().numpy() for g in range(n)], axis=1)
-        assert np.array_equal(got, one["profiles"])
+        from parity import _row_err
+        assert np.array_equal(got == -99999.0, one["profiles"] == -99999.0)
+        assert max(float(_row_err(got[q], one["profiles"][q]).max()) for q in range(len(prof))) < 1e-10
         for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"):
             host_free(out[k])
     finally:

@@ -49,17 +49,36 @@ def test_single_galaxy_list_and_namelist_overrides(exe, tmp_path):
 def test_resume_filtering_from_log_completed(exe, tmp_path):
     """The output file doubles as checkpoint (distributor.f90:150-156): galaxies whose Log/completed flag
     is set are skipped (IO_hdf5.f90:244-266); --restart ignores the file, --stop-after N is the graceful
-    stop.  Host logic only (--dry-run); the file is written by the HDF5 writer probe."""
+    stop.  Host logic only (--dry-run); the file is written by the HDF5 writer probe the way a killed run
+    leaves it: galaxies 1-50 and 101-150 completed, the rest never written (fill value)."""
     probe, out = str(tmp_path / "probe"), str(tmp_path / "out.hdf5")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", probe, os.path.join(ROOT, "tests", "hdf5_writer_probe.cpp"), "-lz"])
-    subprocess.check_call([probe, out, "7", "11", "5"], stdout=subprocess.DEVNULL)   # galaxies 1..7, completed: 1, 4, 7
-    ids = [str(i) for i in range(1, 8)]
-    run = lambda *extra: subprocess.run([exe, PARAMS, *ids, "--out", out, "--dry-run", *extra], cwd=ROOT, capture_output=True, text=True)
-    assert "resume yes: 3 of 7 galaxies completed, 4 to solve now" in run().stdout
-    assert "resume yes: 3 of 7 galaxies completed, 2 to solve now" in run("--stop-after", "2").stdout
-    assert "resume no: 0 of 7 galaxies completed, 7 to solve now" in run("--restart").stdout
-    other = subprocess.run([exe, PARAMS, "1", "2", "3", "--out", out, "--dry-run"], cwd=ROOT, capture_output=True, text=True)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-o", probe, os.path.join(ROOT, "tests", "hdf5_writer_probe.cpp"), "-lz"])
+    subprocess.check_call([probe, "write1", out, "196", "101", "40", "50", "chunked"], stdout=subprocess.DEVNULL)
+    run = lambda *extra: subprocess.run([exe, PARAMS, "--out", out, "--dry-run", *extra], cwd=ROOT, capture_output=True, text=True)
+    assert "resume yes: 100 of 196 galaxies completed, 96 to solve now" in run().stdout
+    assert "resume yes: 100 of 196 galaxies completed, 2 to solve now" in run("--stop-after", "2").stdout
+    assert "resume no: 0 of 196 galaxies completed, 196 to solve now" in run("--restart").stdout
+    assert "resume yes: 2 of 4 galaxies completed, 2 to solve now" in run("50", "51", "100", "101").stdout   # a sub-list
+    # a file written for another grid cannot be extended
+    p = tmp_path / "p.in"
+    p.write_text(open(os.path.join(ROOT, PARAMS)).read().replace("&grid_parameters", "&grid_parameters\n  p_nx_ref = 51"))
+    other = subprocess.run([exe, str(p), "--out", out, "--dry-run"], cwd=ROOT, capture_output=True, text=True)
     assert other.returncode == 1 and "cannot resume" in other.stderr and "--restart" in other.stderr
+
+
+def test_unimplemented_switch_is_rejected_not_ignored(exe, tmp_path):
+    """A namelist that sets a physics switch the CUDA path does not implement must fail loudly: running
+    default physics under a non-default label would stamp wrong parameters into the output file."""
+    base = open(os.path.join(ROOT, PARAMS)).read()
+    for key, val in (("Krause", ".false."), ("p_neumann_boundary_condition_rmax", ".true."), ("Alp_squared", "T"), ("p_sech2_profile", ".true.")):
+        p = tmp_path / "bad.in"
+        p.write_text(base + f"\n&dynamo_parameters\n  {key} = {val}\n/\n")
+        r = subprocess.run([exe, str(p), "--dry-run"], cwd=ROOT, capture_output=True, text=True)
+        assert r.returncode == 1 and key.lower() in r.stderr.lower() and "not implemented" in r.stderr, key
+    ok = tmp_path / "ok.in"    # the default value spelled out, an observables key and an unknown key: accepted with warnings
+    ok.write_text(base + "\n&dynamo_parameters\n  Krause = .true.\n  p_no_such_key = 3\n/\n&observables_parameters\n  p_obs_CR_alpha = 2d0\n/\n")
+    r = subprocess.run([exe, str(ok), "--dry-run"], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and "unknown key p_no_such_key" in r.stderr and "p_obs_cr_alpha has no effect" in r.stderr
 
 
 def test_no_cpu_fallback(exe):
@@ -72,50 +91,69 @@ def test_no_cpu_fallback(exe):
 
 @pytest.mark.gpu
 def test_driver_end_to_end_example(exe, oracle, example_input, tmp_path):
-    """BASELINE configs 1/2 through the real file format: single-galaxy mode and a full run."""
+    """BASELINE configs 1/2 through the real file formats: the reference's parameter file and HDF5 input
+    in, the reference's HDF5 output layout out (chunked + deflate, one row per galaxy of the input file,
+    fill value -1d50 where nothing was written), several checkpoint cycles, single-galaxy mode, and an
+    interrupted run that is extended in place."""
+    import h5spec
+    from magnetizer_b200.hdf5_min import H5File
     from parity import RTOL
     t, inputs = example_input
-    out = str(tmp_path / "example_output.npz")
-    log = subprocess.check_output([exe, PARAMS, "--devices", "0,0", "--chunk", "16", "--out", out], cwd=ROOT, text=True)
-    assert "196 galaxies x 40 snapshots" in log
-    d = np.load(out)
-    assert d["Output/Br"].shape == (196, 101, 40) and d["Log/status"].shape == (196, 40)
+    FILL = -1e50
+    base = open(os.path.join(ROOT, PARAMS)).read().replace(
+        "&io_parameters", "&io_parameters\n  p_ncheckpoint = 60\n  p_IO_number_of_galaxies_in_chunks = 50")
+    params = tmp_path / "cycles.in"
+    params.write_text(base)
+    out = str(tmp_path / "example_output.hdf5")
+    log = subprocess.check_output([exe, str(params), "--devices", "0,0", "--out", out], cwd=ROOT, text=True)
+    assert "196 galaxies x 40 snapshots" in log and "2 flush(es)" in log       # cycles of 100 + 96 galaxies (blocks of 50)
+    objs = h5spec.walk(out)                                                    # the format-specification walker
+    assert objs["trailing_bytes"] == 0
+    br = objs["/Output/Br"]
+    assert br.shape == (196, 101, 40) and br.chunk == (50, 101, 1) and br.filters == [(1, [6])] and br.nchunks == 4 * 40
+    d = H5File(out)
     ids = np.arange(1, 197, dtype=np.int32)
     ora = oracle.solve_batch(oracle.default_params(), ids, t, inputs, profiles=("Br", "h", "rkpc"), scalars=("Bmax",))
     for k, name, fac in ((0, "Br", 1.0), (1, "h", 1e3), (2, "r", 1.0)):
         want = np.transpose(ora["profiles"][k], (0, 2, 1))
         want = np.where(want == -99999.0, want, want * fac)
         got = d["Output/" + name]
+        assert np.array_equal(got, objs["/Output/" + name].data)
         scale = np.abs(want).max(axis=1, keepdims=True)
         assert np.all(np.abs(got - want) <= RTOL * np.maximum(scale, 1e-300)), name
     assert np.array_equal(d["Log/status"].view("S1").reshape(196, 40), ora["status"])
-    assert np.array_equal(d["Log/nsteps"], ora["nsteps"].astype(float))
-    # single-galaxy mode (Fortran gal_id = 1), written as HDF5 in the reference's layout
-    # (mag_hdf5_writer.hpp) and read back with the pure-python reader
-    from magnetizer_b200.hdf5_min import H5File
-    out1 = str(tmp_path / "example_output_gal1.hdf5")
-    subprocess.check_call([exe, PARAMS, "1", "--out", out1], cwd=ROOT, stdout=subprocess.DEVNULL)
+    assert np.array_equal(d["Log/nsteps"].ravel(), ora["nsteps"].astype(float))
+    assert d["Log/nsteps"].shape == (196, 1) and d["Log/completed"].ravel().tolist() == [1.0] * 196
+    assert d.attrs("Output/Br")["Units"] == "microgauss" and d.attrs("Output/h")["Description"] == "Disk scaleheight"
+    # single-galaxy mode (Fortran gal_id = 24): the datasets still have one row per galaxy of the input file
+    out1 = str(tmp_path / "example_output_gal24.hdf5")
+    subprocess.check_call([exe, PARAMS, "24", "--out", out1], cwd=ROOT, stdout=subprocess.DEVNULL)
     f1 = H5File(out1)
     assert f1.keys("/") == ["Log", "Output"] and "Br" in f1.keys("Output") and "r" in f1.keys("Output")
-    assert np.array_equal(f1["Output/Br"][0], d["Output/Br"][0]) and f1["Log/gal_id"].tolist() == [1]
-    assert f1["Output/Br"].shape == (1, 101, 40) and f1["Log/status"].shape == (1, 40) and f1["Log/nsteps"].shape == (1, 1)
-    assert f1["Log/status"].tobytes() == ora["status"][0].tobytes()
-    assert f1.attrs("Output/Br")["Units"] == "microgauss" and f1.attrs("Output/h")["Description"] == "Disk scaleheight"
-    # interrupted run + resume == straight run (the output file is the checkpoint)
+    b1 = f1["Output/Br"]
+    assert b1.shape == (196, 101, 40) and np.array_equal(b1[23], d["Output/Br"][23])
+    assert np.all(b1[:23] == FILL) and np.all(b1[24:] == FILL)                 # IO_hdf5.f90:44,979
+    comp = f1["Log/completed"].ravel()
+    assert comp[23] == 1.0 and np.all(np.delete(comp, 23) == FILL)
+    assert f1["Log/status"][23].tobytes() == ora["status"][23].tobytes() and f1["Log/status"][0].tobytes() == b"\0" * 40
+    # interrupted run + resume == straight run (the output file is the checkpoint and is extended in place)
     part, full = str(tmp_path / "resumed.hdf5"), str(tmp_path / "straight.hdf5")
     gl = ["3", "24", "60", "101"]
     log_a = subprocess.check_output([exe, PARAMS, *gl, "--out", part, "--stop-after", "2"], cwd=ROOT, text=True)
     fa = H5File(part)
-    assert "(0 already completed, 2 to solve)" in log_a and fa["Log/completed"].ravel().tolist() == [1.0, 1.0, 0.0, 0.0]
-    assert fa["Log/status"][2].tobytes() == b"-" * 40 and np.all(fa["Output/Br"][2:] == -99999.0)
+    ca = fa["Log/completed"].ravel()
+    assert "(0 already completed, 2 to solve)" in log_a and ca[[2, 23]].tolist() == [1.0, 1.0] and ca[59] == FILL and ca[100] == FILL
+    size_a = os.path.getsize(part)
     log_b = subprocess.check_output([exe, PARAMS, *gl, "--out", part], cwd=ROOT, text=True)
-    assert "(2 already completed, 2 to solve)" in log_b
+    assert "(2 already completed, 2 to solve)" in log_b and os.path.getsize(part) > size_a
     subprocess.check_call([exe, PARAMS, *gl, "--out", full], cwd=ROOT, stdout=subprocess.DEVNULL)
+    h5spec.walk(part)
     fb, fc = H5File(part), H5File(full)
-    assert fb["Log/completed"].ravel().tolist() == [1.0] * 4 and fb.keys("Output") == fc.keys("Output")
+    assert fb["Log/completed"].ravel()[[2, 23, 59, 100]].tolist() == [1.0] * 4 and fb.keys("Output") == fc.keys("Output")
     for k in fc.keys("Output"):
         assert np.array_equal(fb["Output/" + k], fc["Output/" + k]), k
     assert fb["Log/status"].tobytes() == fc["Log/status"].tobytes() and np.array_equal(fb["Log/nsteps"], fc["Log/nsteps"])
     root = f1.attrs("/")
     assert "P_NX_REF=101," in root["grid_parameters"] and root["run_parameters"].startswith("&RUN_PARAMETERS ")
     assert float(re.search(r"P_COURANT_V=([^,]+),", root["run_parameters"])[1]) == 0.09000000357627869
+    assert 'P_OUTFLOW_TYPE="no_outflow"' in root["outflow_parameters"] and "P_IO_COMPRESSION=T" in root["io_parameters"]

@@ -68,26 +68,21 @@ def main():
                 same = all(np.array_equal(ref[k], snap[k]) for k in ("nsteps", "point_stages"))
                 err = np.abs(ref["profiles"] - snap["profiles"]).max()
                 print(f"      vs light only: exact fields {'identical' if same else 'DIFFER'}, max abs profile difference {err:.2e}", flush=True)
-        s.set_heavy_policy(mode=1, alpha=0.8)
+        s.set_heavy_policy(mode=1, alpha=1.5)
 
     if "cfg2" in cases:
         ids = np.arange(1, base.shape[1] + 1, dtype=np.int32)
-        modes("config 2 (196 example galaxies)", ids, base, alphas=(0.5, 0.8, 1.2))
+        modes("config 2 (196 example galaxies)", ids, base, alphas=(1.5,))
     if "share" in cases:
         n = 12500
         syn = synthetic_histories(base, n, first=20000)
         ids = galaxy_ids(n, first=20000)
-        modes("config 3 share (12500 synthetic)", ids, syn, alphas=(0.4, 0.6, 0.8, 1.0, 1.3))
-        os.environ["MAG_EVOLVE_PDL"] = "0"
-        s2 = S.DynamoSolver(device=0)
-        del os.environ["MAG_EVOLVE_PDL"]
-        r, tm, wall = timed(s2, ids, t, syn)
-        report("config 3 share split alpha=0.8, two streams", s2, r, tm, wall, n)
-        s2.close()
+        modes("config 3 share (12500 synthetic)", ids, syn, alphas=tuple(float(a) for a in os.environ.get("MAG_PROBE_ALPHAS", "1.0,1.5,2.0,2.5").split(",")))
+    if "mid" in cases:
         n = 25000
         syn = synthetic_histories(base, n, first=40000)
         ids = galaxy_ids(n, first=40000)
-        modes("25000 synthetic", ids, syn, alphas=(0.8,))
+        modes("25000 synthetic", ids, syn, alphas=(1.5,))
     if "tput" in cases:
         for copies in (1, 148, 444, 1184):
             inp = np.ascontiguousarray(np.repeat(base[:, 4:5, :], copies, axis=1))
@@ -98,7 +93,35 @@ def main():
                 s.set_heavy_policy(mode=mode)
                 r, tm, wall = timed(s, ids, t, inp)
                 report(f"uniform gal 5 x{copies} (3 snapshots) {name}", s, r, tm, wall, copies)
-        s.set_heavy_policy(mode=1, alpha=0.8)
+        s.set_heavy_policy(mode=1, alpha=1.5)
+    if "prof" in cases:
+        n = 12500
+        syn = synthetic_histories(base, n, first=20000)
+        ids = galaxy_ids(n, first=20000)
+        s.set_heavy_policy(mode=1, alpha=1.5)
+        r, tm, wall = timed(s, ids, t, syn, reps=3)
+        report("profile phase probe (12500 synthetic)", s, r, tm, wall, n)
+    if "part" in cases:
+        # the multi-GPU partition on ONE GPU: one or two host threads (contexts) per GPU, chunk sizes
+        n = int(os.environ.get("MAG_PROBE_PART_N", "50000"))
+        syn = synthetic_histories(base, n, first=100000)
+        ids = galaxy_ids(n, first=100000)
+        for threads in ("1", "2"):
+            os.environ["MAG_PARTITION_THREADS_PER_GPU"] = threads
+            part = S.Partition([0])
+            del os.environ["MAG_PARTITION_THREADS_PER_GPU"]
+            out = part.alloc_outputs(n, t.size, PROF, SCAL, pinned=True)
+            for chunk in (6250, 12500, 25000):
+                part.solve(ids[:2000], t, np.ascontiguousarray(syn[:, :2000]), chunk=1000, profiles=PROF, scalars=SCAL)
+                t0 = time.perf_counter()
+                r = part.solve(ids, t, syn, chunk=chunk, profiles=PROF, scalars=SCAL, out=out)
+                dt = time.perf_counter() - t0
+                st = part.stats()
+                print(f"partition 1 GPU x {threads} thread(s), {n} galaxies, chunk {chunk:6d}: {dt * 1e3:8.1f} ms  {n / dt:8.0f} gal/s  "
+                      f"kernel-busy {st['busy_ms'][0]:8.1f} ms", flush=True)
+            for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"):
+                S.host_free(out[k])
+            part.close()
     if "big" in cases:
         n = 40000
         syn = synthetic_histories(base, n)
