@@ -296,7 +296,7 @@ void mag_host_free(void *p);
 /*
  * Multi-GPU form: replaces the MPI master/worker farm of jobs_distribute
  * (source/distributor.f90:253-384) for this operator.  The catalogue is cut into chunks of
- * `chunk` galaxies (chunk <= 0: four chunks per device); GPU number d of `devices[ndev]` owns the chunks k with k % ndev == d
+ * `chunk` galaxies (chunk <= 0: one chunk per device, cut into equal pieces of at most 25 000); GPU number d of `devices[ndev]` owns the chunks k with k % ndev == d
  * (static share) and steals unclaimed chunks from the tails of the other GPUs' shares when its
  * own is exhausted.  Every GPU is driven by TWO host threads with one solver context each, so
  * that the profile phase and the head of one chunk fill the SMs that the tail of the previous
@@ -332,7 +332,7 @@ int mag_partition_solve_device(mag_partition_t *part, int32_t ngal, const int32_
                                int32_t n_scalar_q, const int32_t *scalar_q, const mag_outputs_t *d_out,
                                int32_t chunk, int32_t *chunks_done, int32_t *chunks_stolen, int32_t *owner);
 /* Of the last solve on this partition: the chunk size used (chunk <= 0 in a solve call selects it
- * automatically: four chunks per device), kernel launches per device and the device time
+ * automatically), kernel launches per device and the device time
  * (ms, CUDA events) spent inside the kernels of each device's chunks -- where two chunks of a
  * device overlap, both count. */
 int mag_partition_stats(mag_partition_t *part, int32_t *chunk_used, int64_t *launches, double *busy_ms);

@@ -162,11 +162,14 @@ void worker_main(mag_partition* P, int wi) {
 int run_partition(mag_partition* P, int32_t* chunks_done, int32_t* chunks_stolen) {
   Job& J = P->job;
   if (J.chunk <= 0) {
-    // automatic: four chunks per device -- large enough that a chunk's own work covers the latency of its
-    // longest history, small enough that the threads of a device always have a next chunk to overlap
-    long long c = ((long long)J.ngal + 4LL * P->ndev - 1) / (4LL * P->ndev);
+    // automatic: one chunk per device, cut into equal pieces of at most 25 000 galaxies.  Measured on one
+    // B200 (profiles/r2_bench.md): a chunk must be large for its own work to cover the latency of its
+    // longest histories (12 500 galaxies: 9.9 k galaxies/s; 2 x 6 250: 8.2 k), and beyond ~25 000 the
+    // cost-ordered queue of one solve runs its large-grid histories all at once and loses 10 %
+    // (4 x 25 000: 11.5 k galaxies/s, 1 x 100 000: 10.7 k)
+    long long c = ((long long)J.ngal + P->ndev - 1) / P->ndev;
+    if (c > 25000) { const long long pieces = (c + 24999) / 25000; c = (c + pieces - 1) / pieces; }
     if (c < 256) c = 256;
-    if (c > 32768) c = 32768;
     J.chunk = (int32_t)c;
   }
   J.nchunks = (J.ngal + J.chunk - 1) / J.chunk;

@@ -32,9 +32,12 @@ def _mask_failed_runs(got: dict, want: dict):
     tripped, dynamo.f90:222-257).  Such a run is a numerical instability that grows out of rounding noise:
     the step at which it crosses the 1e8 / 1000 thresholds -- and with it the accumulated time, the number of
     stages, occasionally the snapshot that ends up 'i' -- depends on the last bit of every operation, also
-    between two builds of the reference (profiles/r2_sensitivity.md).  For these galaxies parity is required
-    of everything up to the last snapshot before the first failure, of the failure itself being reported
-    (same flag; first failing snapshot within one of the reference's), and of nothing after it.
+    between two builds of the reference (profiles/r2_sensitivity.md: the -O2 build of the oracle with and
+    without FMA contraction disagree on the stage count of 9 of 35 failed runs with p_use_Pdm = F).  The
+    growing mode is already visible in the snapshot before the one that fails (|B| doubles there), so for
+    these galaxies parity is required of everything up to TWO snapshots before the first failure, of the
+    failure itself being reported (same flag; first failing snapshot within one of the reference's), and of
+    nothing after it.
     Returns copies of (got, want) in which the rows from the first failure on are blanked identically."""
     gs, ws = np.asarray(got["status"]).view("S1"), np.asarray(want["status"]).view("S1")
     gf, wf = np.asarray(got["flags"]), np.asarray(want["flags"])
@@ -49,7 +52,7 @@ def _mask_failed_runs(got: dict, want: dict):
             assert bad.size, f"galaxy index {g}: retry flag without an 'm' / 'i' snapshot"
             first.append(int(bad[0]))
         assert abs(first[0] - first[1]) <= 1, f"galaxy index {g}: first failing snapshot {first[0]} vs {first[1]}"
-        s0 = min(first)
+        s0 = max(min(first) - 1, 0)
         for d in (g2, w2):
             d["status"][g, s0:] = b"?"
             d["profiles"][:, g, s0:] = 0.0

@@ -97,7 +97,10 @@ def test_automatic_chunk_size(stub_solver):
     part = S.Partition([0, 1])
     try:
         r = part.solve(ids, t, inp, chunk=0, profiles=("Br",), scalars=())
-        assert part.stats()["chunk"] == 625 and r["chunks_done"].sum() == 8      # four chunks per device
+        assert part.stats()["chunk"] == 2500 and r["chunks_done"].sum() == 2     # one chunk per device
+        big_ids, _, big_in = catalogue(60001, nz=1)
+        part.solve(big_ids, t[:1], big_in, chunk=0, profiles=("Br",), scalars=())
+        assert part.stats()["chunk"] == 15001                                    # 30 001 per device in two equal pieces
         part.solve(ids[:300], t, np.ascontiguousarray(inp[:, :300]), chunk=0, profiles=("Br",), scalars=())
         assert part.stats()["chunk"] == 256                                      # floor
     finally:
