@@ -320,17 +320,17 @@ def run_b200(args):
                "sample": f"{len(idx)} galaxies = every {G // len(idx)}-th of the catalogue, one pass, {cdt:.1f} s; the e2e arm's rows "
                          f"of those galaxies checked against it (worst row-relative error {max(rep.values()):.1e})"}
 
-    cfg = base_config(G, nz)
-    cfg.update({"partition": f"mag_partition_solve: {ndev} GPU(s) x 2 host threads, chunks of {pstats['chunk']} galaxies, "
-                             "static share + stealing, no collective",
-                "chunks_done": st_last["chunks_done"].tolist(), "chunks_stolen": st_last["chunks_stolen"].tolist(),
-                "gpu_busy_ms_per_step": [round(x, 1) for x in busy_ms],
-                "l2": "256 MiB flush write on every GPU between timed steps",
-                "point_stages_per_galaxy": W_total / G, "galaxies_with_error": n_err})
+    cfg = base_config(G, nz)       # the same dict in both arms (--impl reference prints it too)
+    partition = {"how": f"mag_partition_solve_device / mag_partition_solve: {ndev} GPU(s) x 2 host threads, chunks of {pstats['chunk']} "
+                        "galaxies, static share + stealing, no collective; rank 0 drives every GPU",
+                 "chunks_done": st_last["chunks_done"].tolist(), "chunks_stolen": st_last["chunks_stolen"].tolist(),
+                 "gpu_busy_ms_per_step": [round(x, 1) for x in busy_ms],
+                 "l2": "256 MiB flush write on every GPU between timed steps",
+                 "point_stages_per_galaxy": W_total / G, "galaxies_with_error": n_err}
     line = {
         "metric": METRIC, "value": G / (ms_dev * 1e-3), "unit": "galaxies/s", "n_gpus": ndev,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "partition": partition,
         "e2e": {"value": G / (ms_e2e * 1e-3), "unit": "galaxies/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "steps": e2e_steps,
                 "chunks_done": r_e2e["chunks_done"].tolist(), "chunks_stolen": r_e2e["chunks_stolen"].tolist(),

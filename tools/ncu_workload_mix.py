@@ -14,6 +14,7 @@ from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories  # noqa: E
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    nsteps_max = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # > 0: cap the steps per snapshot, so that no single history sets the kernel time
     d = np.load(os.path.join(ROOT, "tests", "golden", "example_input.npz"))
     t, base = d["t_gyr"], d["inputs"]
     inputs = synthetic_histories(base, n, first=196)
@@ -23,7 +24,11 @@ if __name__ == "__main__":
         if valid.size > k:
             inputs[0, g, valid[k]:] = -1.0e10
     inputs = np.ascontiguousarray(inputs)
-    s = DynamoSolver(device=0)
+    from magnetizer_b200.solver import default_params
+    p = default_params()
+    if nsteps_max > 0:
+        p.p_nsteps_max = nsteps_max
+    s = DynamoSolver(params=p, device=0)
     prof, scal = ("Br", "Bp", "alp_m", "h", "n"), ("Bmax",)
     s.run(ids[:8], t, np.ascontiguousarray(inputs[:, :8]), profiles=prof, scalars=scal)
     r = s.run(ids, t, inputs, profiles=prof, scalars=scal)
