@@ -302,7 +302,7 @@ def run_b200(args):
     # ---- CPU baseline on the host cores: the oracle port on a bounded sample of the same catalogue,
     # and the GPU rows of those galaxies checked against it
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and ndev == 1:     # rank 0 at N = 1 only
         from oracle import oracle_lib
         oracle_lib.build()
         idx = cpu_sample_ids(G)

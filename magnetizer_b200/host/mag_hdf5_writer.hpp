@@ -62,7 +62,7 @@ class Hdf5Writer {
     int gals_per_chunk = 1000;      // p_IO_number_of_galaxies_in_chunks
     bool compression = true;        // p_IO_compression (requires chunking)
     int level = 6;                  // p_IO_compression_level
-    int threads = 0;                // deflate threads (0: hardware concurrency, at most 16)
+    int threads = 0;                // deflate threads (0: hardware concurrency, at most 32)
   };
   static constexpr double kFill = -1e50;   // INVALID, IO_hdf5.f90:44
 
@@ -174,7 +174,7 @@ class Hdf5Writer {
         enc[(size_t)il].assign(raw.data(), raw.size());
       }
     };
-    int nt = opt_.threads > 0 ? opt_.threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    int nt = opt_.threads > 0 ? opt_.threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
     if ((uint64_t)nt > nlast) nt = (int)nlast;
     if (nt <= 1 || !opt_.compression) {
       for (uint64_t il = 0; il < nlast; il++) build(il);

@@ -81,6 +81,83 @@ def test_unimplemented_switch_is_rejected_not_ignored(exe, tmp_path):
     assert r.returncode == 0 and "unknown key p_no_such_key" in r.stderr and "p_obs_cr_alpha has no effect" in r.stderr
 
 
+@pytest.fixture(scope="module")
+def stub_exe():
+    """The real driver linked against the CPU fake of the single-GPU entry points (tests/partition_stub.cpp +
+    the real csrc/mag_partition.cu): everything of the driver except the physics runs without a GPU."""
+    from test_partition_host import BUILD, build_stub
+    build_stub()
+    out = os.path.join(BUILD, "Magnetizer_stub")
+    src = os.path.join(ROOT, "magnetizer_b200", "host", "magnetizer_main.cpp")
+    deps = [src] + [os.path.join(ROOT, "magnetizer_b200", "host", h) for h in ("mag_hdf5_writer.hpp", "mag_hdf5_reader.hpp", "mag_namelist.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps + [os.path.join(BUILD, "libpartstub.so")]):
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O1", "-std=c++17", "-o", out, src, "-L" + BUILD, "-lpartstub", "-lz",
+                               "-Xlinker", "-rpath", "-Xlinker", BUILD], stderr=subprocess.DEVNULL)
+    return out
+
+
+def stub_profile(name_id, ids, inputs, nz, fac=1.0):
+    """what tests/partition_stub.cpp writes for profile quantity name_id, in the file's (ngal, nx, nz) layout and units"""
+    i = np.arange(101) * 1e-3
+    v = ids[:, None, None] * 1000.0 + name_id * 10.0 + inputs[0][ids - 1][:, :, None] + i[None, None, :]   # (n, nz, nx)
+    return np.transpose(v, (0, 2, 1)) * fac
+
+
+def test_driver_cycles_layout_resume_and_stop_file(stub_exe, example_input, tmp_path):
+    """The driver's side of jobs_distribute + write_output (distributor.f90:253-337, output.f90:23-236) with the
+    physics faked: checkpoint cycles with a flush each, the reference's file layout (one row per galaxy of the input
+    file, chunked + deflate, fill -1d50), sparse galaxy lists, a stop after a cycle (STOP file) and the in-place resume
+    that merges new galaxies into blocks an earlier invocation had partly filled."""
+    import h5spec
+    from magnetizer_b200.abi import PROFILE_ID
+    t, inputs = example_input
+    FILL = -1e50
+    base = open(os.path.join(ROOT, PARAMS)).read().replace('"tests/golden/', '"' + ROOT + '/tests/golden/').replace("'tests/golden/", "'" + ROOT + "/tests/golden/").replace(
+        "&io_parameters", "&io_parameters\n  p_ncheckpoint = 60\n  p_IO_number_of_galaxies_in_chunks = 50")
+    params = tmp_path / "cycles.in"
+    params.write_text(base)
+    out = str(tmp_path / "stub_output.hdf5")
+    run = lambda *a: subprocess.run([stub_exe, str(params), "--devices", "0,1", "--out", out, *a], cwd=tmp_path, capture_output=True, text=True)
+    # 1. a sparse list first: galaxies 3, 24, 60, 101, 150 -> one cycle (fewer than p_ncheckpoint galaxies), blocks 0, 1, 2
+    r = run("3", "24", "60", "101", "150")
+    assert r.returncode == 0 and "1 flush(es)" in r.stdout, r.stderr
+    objs = h5spec.walk(out)
+    ids = np.array([3, 24, 60, 101, 150])
+    br = objs["/Output/Br"]
+    assert br.shape == (196, 101, 40) and br.chunk == (50, 101, 1) and br.filters == [(1, [6])] and br.nchunks == 3 * 40
+    assert np.array_equal(br.data[ids - 1], stub_profile(PROFILE_ID["Br"], ids, inputs, 40))
+    rest = np.setdiff1d(np.arange(196), ids - 1)
+    assert np.all(br.data[rest] == FILL)                                       # never written: the fill value (IO_hdf5.f90:44,979)
+    assert np.array_equal(objs["/Output/h"].data[ids - 1], stub_profile(PROFILE_ID["h"], ids, inputs, 40, 1e3))   # kpc -> pc (output.f90)
+    assert np.array_equal(objs["/Output/r"].data[ids - 1], stub_profile(PROFILE_ID["rkpc"], ids, inputs, 40))
+    comp = objs["/Log/completed"].data[:, 0]
+    assert np.all(comp[ids - 1] == 1.0) and np.all(comp[rest] == FILL)
+    assert objs["/Log/status"].data[2].tobytes() == b"M" * 40 and objs["/Log/status"].data[0].tobytes() == b"\0" * 40
+    assert np.array_equal(objs["/Log/nsteps"].data[ids - 1, 0], ids.astype(float))
+    # 2. the whole catalogue, stopped by a STOP file after its first cycle (blocks 0-1: the galaxies not yet completed there)
+    (tmp_path / "STOP").write_text("")
+    r = run()
+    assert r.returncode == 0 and "STOP file found" in r.stdout and "(5 already completed, 191 to solve)" in r.stdout
+    os.remove(tmp_path / "STOP")
+    comp = h5spec.walk(out)["/Log/completed"].data[:, 0]
+    assert np.all(comp[:100] == 1.0) and comp[100] == 1.0 and comp[149] == 1.0 and np.all(np.delete(comp[101:], 48) == FILL)
+    # 3. resume: the rest (blocks 2 and 3 in one cycle); rows of all three invocations are there, the file grew in place
+    size2 = os.path.getsize(out)
+    r = run()
+    assert r.returncode == 0 and "(102 already completed, 94 to solve)" in r.stdout and "1 flush(es)" in r.stdout
+    assert os.path.getsize(out) > size2
+    objs = h5spec.walk(out)
+    assert objs["trailing_bytes"] == 0
+    all_ids = np.arange(1, 197)
+    assert np.array_equal(objs["/Output/Br"].data, stub_profile(PROFILE_ID["Br"], all_ids, inputs, 40))
+    assert np.all(objs["/Log/completed"].data == 1.0) and objs["/Output/Br"].nchunks == 4 * 40
+    from magnetizer_b200.hdf5_min import H5File
+    assert np.array_equal(H5File(out)["Output/Bmax"], objs["/Output/Bmax"].data)
+    # 4. nothing left to do
+    r = run()
+    assert r.returncode == 0 and "(196 already completed, 0 to solve)" in r.stdout
+
+
 def test_no_cpu_fallback(exe):
     import torch
     if torch.cuda.is_available():
