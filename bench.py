@@ -266,8 +266,8 @@ def run_b200(args):
     d2h = sum(out[k].nbytes for k in ("profiles", "scalars", "status", "nsteps", "error", "point_stages", "flags"))
     assert int(r_e2e["point_stages"].sum()) == W_total, "e2e and HBM-resident arms disagree"
 
-    # ---- roofline of the evolve kernels: one context, one stream, CUDA events (GPU 0, its 1/N of the catalogue)
-    Gs = G // ndev
+    # ---- roofline of the evolve kernels: one context, one stream, CUDA events (GPU 0, one chunk of the partition)
+    Gs = min(G, int(pstats["chunk"]))
     solver = DynamoSolver(device=0)
     with torch.cuda.device(devs[0]):
         r0 = res[0]
@@ -285,6 +285,7 @@ def run_b200(args):
         solver.device_status()
         tim = solver.last_timing()
         W_slice = int(r0["ps"][:Gs].sum().item())
+        snaps_slice = int((r0["status"][:Gs] != ord("-")).sum().item())     # galaxy-snapshots the launch processed
         info = solver.info()
         fp64_peak = solver.measure_fp64_peak(5)
     ms_evolve = tim["ms_kernels"] - tim["ms_profile_phase"]
@@ -338,7 +339,9 @@ def run_b200(args):
         "gpu_launches": int(launches_step * args.steps),
         "roofline": {"bound": "fp64", "achieved": flops / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                      "frac": flops / fp64_peak if fp64_peak else None,
-                     "traffic": ncu.get("dram_bytes_per_launch"),
+                     # DRAM bytes of the launch: ncu's dram__bytes_read + dram__bytes_write per galaxy-snapshot (records read
+                     # once, output rows written once, workspace write-backs) x the galaxy-snapshots of this launch
+                     "traffic": (ncu["dram_bytes_per_galaxy_snapshot"] * snaps_slice) if "dram_bytes_per_galaxy_snapshot" in ncu else None,
                      "kernel": "k_evolve (+ k_evolve_heavy, concurrent)", "flop_per_point_stage": FLOP_PER_POINT_STAGE,
                      "point_stages_per_launch": W_slice, "galaxies_per_launch": Gs, "kernel_ms": ms_evolve,
                      "share_of_step": ms_evolve / tim["ms_kernels"], "profile_phase_ms": tim["ms_profile_phase"],
