@@ -139,7 +139,7 @@ typedef struct mag_params {
   int32_t p_halo_contraction;     /* 1 */
   int32_t p_enable_P2;            /* 0 */
   int32_t Dyn_quench;             /* 1 */
-  int32_t Alg_quench;             /* 0 */
+  int32_t Alg_quench;             /* 0; 1 is implemented on the generic (any-nx) path: alp = alp_k/(1+B^2/Beq^2), gutsdynamo.f90:202-203 */
   int32_t Damp;                   /* 0 */
   int32_t lFloor;                 /* 1 */
   int32_t p_space_varying_floor;  /* 1 */

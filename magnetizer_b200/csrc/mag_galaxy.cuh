@@ -903,6 +903,8 @@ __device__ inline void pde_generic(Gal& G) {
   const double *Gc = G.A(A_G), *alp_k = G.A(A_ALPK), *sg = G.A(A_SIGN);
   double *p0 = G.A(A_P0), *p1 = G.A(A_P1), *p2 = G.A(A_P2), *alp = G.A(A_ALP);
   const double Rk = G.a->P.R_kappa;
+  const bool alg = G.a->P.Alg_quench != 0;
+  const double *bz = G.A(A_BZ), *beq = G.A(A_BEQ);
   for (int i = G.lane; i < nx; i += 32) {
     const double Br = f0[i], Bp = f1[i], am = f2[i];
     const double dBr = xder_at(f0, i, nx, fac1), d2Br = xder2_at(f0, i, nx, fac2);
@@ -911,7 +913,9 @@ __device__ inline void pde_generic(Gal& G) {
     const double d2am = xder2_at(f2, i, nx, fac2);
     if (i == MAG_NGHOST) dam = 0.0;
     const double ir = cIR[i], c1 = cC1[i], cr = cCR[i];
-    const double a = alp_k[i] + am;
+    // total alpha: dynamical quenching, or -- Alg_quench -- alp_k/(1 + Bsqtot/Beq^2) with Bsqtot = Br^2+Bp^2+Bzmod^2
+    // (gutsdynamo.f90:199-209; Bzmod is the estimate of the start of the step, dynamo.f90:179)
+    const double a = alg ? alp_k[i] / (1.0 + (Br * Br + Bp * Bp + bz[i] * bz[i]) / (beq[i] * beq[i])) : alp_k[i] + am;
     alp[i] = a;
     p0[i] = -c1 * Br - cCA[i] * a * Bp + cr * (d2Br + ir * (dBr - Br * ir));
     p1[i] = Gc[i] * Br - c1 * Bp + cr * (d2Bp + ir * (dBp - Bp * ir)) + sg[i] * cFB[i] * (1.0 + cKDC[i] * a);

@@ -106,6 +106,7 @@ __device__ __noinline__ bool run_steps_generic(Gal& G, int jt0, int nb) {
   const double dtg = G.dt * G.a->U.t0_Gyr;
   for (int jt = jt0; jt < jt0 + nb; jt++) {
     const double this_t = G.t_Gyr + dtg * (double)jt;
+    if (G.a->P.Alg_quench) estimate_Bzmod(G);   // dynamo.f90:179 -- only the algebraic quenching reads it inside pde
     update_floor_sign(G, this_t);
     const bool ok = rk_generic(G);
     impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));

@@ -320,7 +320,7 @@ void mag_params_default(mag_params_t* p) {
 
 static bool params_supported(const mag_params_t& p) {
   return p.abi_version == MAG_ABI_VERSION && p.p_variable_timesteps == 1 && p.p_simplified_pressure == 1 &&
-         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && p.Alg_quench == 0 && p.Damp == 0 &&
+         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && (p.Alg_quench == 0 || p.Alg_quench == 1) && p.Damp == 0 &&
          p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
          p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice == 0 &&
          p.outflow_type >= MAG_OUTFLOW_NONE && p.outflow_type <= MAG_OUTFLOW_SUPERBUBBLE && p.p_nx_ref >= 8 &&
@@ -491,7 +491,9 @@ static int launch_solve(mag_ctx* c, KernelArgs& a, int32_t g0, int32_t n, cudaSt
   a.counter2 = c->d_counter + CNT_LIGHT; a.counter3 = c->d_counter + CNT_HEAVY; a.n_heavy = c->d_counter + CNT_NHEAVY;
   a.n_invalidated = c->d_counter + CNT_INVALIDATED;
   a.cost_total = c->d_arena_top + 1;
-  a.use_fast = c->use_fast;
+  // the register loops hard-wire alp = alp_k + alp_m; algebraic quenching (gutsdynamo.f90:202-203) needs Bzmod in the
+  // RHS at every step and runs on the any-nx generic path
+  a.use_fast = c->P.Alg_quench ? 0 : c->use_fast;
   a.recs = c->d_recs; a.heads = c->d_heads; a.arena = c->d_arena; a.arena_top = c->d_arena_top; a.arena_cap = c->arena_cap;
   a.jobs = c->d_jobs; a.job_count = c->d_job_count; a.jobidx = c->d_jobidx;
   a.pdl_join = c->launch_pdl;

@@ -139,7 +139,7 @@ static void params_default(mag_params_t* p) {
 
 static bool params_supported(const mag_params_t& p) {
   return p.abi_version == MAG_ABI_VERSION && p.p_variable_timesteps == 1 && p.p_simplified_pressure == 1 &&
-         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && p.Alg_quench == 0 &&
+         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && (p.Alg_quench == 0 || p.Alg_quench == 1) &&
          p.Damp == 0 && p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
          p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice == 0 &&
          p.outflow_type >= MAG_OUTFLOW_NONE && p.outflow_type <= MAG_OUTFLOW_SUPERBUBBLE && p.p_nx_ref >= 8 &&
@@ -940,7 +940,9 @@ struct Galaxy {
     double* d1 = dfdt; double* d2 = dfdt + nx; double* d3 = dfdt + 2 * (size_t)nx;
     for (int i = 0; i < nx; i++) {
       const double r = x[i], hh = h[i], et = etat[i], uz = Uz[i];
-      const double a = alp_k[i] + alp_m[i];
+      // gutsdynamo.f90:199-209: Bsqtot = Br**2 + Bp**2 + Bzmod**2; Alg_quench takes precedence over Dyn_quench
+      const double Bsqtot = Br[i] * Br[i] + Bp[i] * Bp[i] + Bzmod[i] * Bzmod[i];
+      const double a = P.Alg_quench ? alp_k[i] / (1.0 + Bsqtot / (Beq[i] * Beq[i])) : alp_k[i] + alp_m[i];
       alp[i] = a;
       const double detatdr = 1.0 / 3 * l[i] * 0.0 + 1.0 / 3 * v[i] * 0.0;  // dvdr = dldr = 0
       const double Dyn_gen = G[i] * a * (hh * hh * hh) / (et * et);

@@ -389,6 +389,28 @@ def test_outflow_models(oracle, example_input, outflow):
     print("outflow", outflow, "worst:", max(rep.values()))
 
 
+def test_algebraic_quenching(oracle, example_input):
+    """Alg_quench = T (gutsdynamo.f90:202-203): alp = alp_k/(1 + (Br^2+Bp^2+Bzmod^2)/Beq^2) replaces the dynamical
+    quenching in the RHS; Bzmod is re-estimated at every step (dynamo.f90:179).  Runs on the any-nx generic path
+    of both evolve kernels."""
+    from magnetizer_b200.solver import DynamoSolver
+    t, inputs = example_input
+    ids, sub = _subset(inputs, [1, 3, 24, 30, 60, 85, 101, 150])
+    p = oracle.default_params()
+    p.Alg_quench = 1
+    ora = oracle.solve_batch(p, ids, t, sub)
+    ref = oracle.solve_batch(oracle.default_params(), ids, t, sub)
+    assert not np.array_equal(ora["profiles"][0], ref["profiles"][0])      # the switch changes Br
+    s = DynamoSolver(params=p, device=0)
+    try:
+        for mode in (0, 2):                                                # one-warp teams, four-warp teams
+            s.set_heavy_policy(mode=mode)
+            rep = compare(s.run(ids, t, sub), ora)
+            print("Alg_quench heavy mode", mode, "worst:", max(rep.values()))
+    finally:
+        s.close()
+
+
 def test_heavy_teams_every_grid_class(oracle, example_input):
     """k_evolve_heavy (four warps per galaxy, mag_rk_fast.cuh): all galaxies forced onto it.  The
     example histories reach nx = 107 .. 330, i.e. the 1-, 2- and 3-points-per-thread loops; results
