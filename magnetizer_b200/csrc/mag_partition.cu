@@ -17,6 +17,7 @@
 // straight into them -- by the kernels themselves when the arrays are page-locked -- in galaxy
 // order: the "host-side gather" of the reference's master is the address computation.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
@@ -70,10 +71,12 @@ struct mag_partition {
   Job job;
   std::atomic<int> rc{MAG_OK};
   std::vector<std::atomic<int>> done, stolen;   // [ndev]
+  std::vector<std::atomic<int>> active;         // [ndev] threads of the device that are inside a chunk right now
+  std::atomic<int> unclaimed{0};                // chunks nobody has taken yet
   std::vector<std::atomic<long long>> launches, busy_us;   // [ndev] kernel launches / device time inside the kernels of the last solve
   std::string err;
 
-  mag_partition(int nd) : done(nd), stolen(nd), launches(nd), busy_us(nd) {}
+  mag_partition(int nd) : done(nd), stolen(nd), active(nd), launches(nd), busy_us(nd) {}
 };
 
 namespace {
@@ -113,9 +116,16 @@ int run_chunk(mag_partition* P, mag_partition::Worker& w, int k) {
 void run_job(mag_partition* P, mag_partition::Worker& w) {
   const Job& J = P->job;
   const int d = w.d, ndev = P->ndev;
-  auto try_claim = [&](int k) { int exp = 0; return J.claimed[k].compare_exchange_strong(exp, 1); };
+  auto try_claim = [&](int k) {
+    int exp = 0;
+    if (!J.claimed[k].compare_exchange_strong(exp, 1)) return false;
+    P->unclaimed--;
+    return true;
+  };
   auto one = [&](int k, bool stolen) {
+    P->active[d]++;
     const int rc = run_chunk(P, w, k);
+    P->active[d]--;
     if (rc != MAG_OK) { fail(P, rc, mag_last_error()); return false; }
     double ms[4] = {0, 0, 0, 0};
     P->launches[d] += mag_last_timing(w.ctx, ms);
@@ -127,18 +137,22 @@ void run_job(mag_partition* P, mag_partition::Worker& w) {
   // 1. the static share, in order (the two threads of a device take alternate chunks of it)
   for (int k = d; k < J.nchunks && P->rc.load() == MAG_OK; k += ndev)
     if (try_claim(k) && !one(k, false)) return;
-  // 2. steal from the tails of the other devices' shares
-  for (int v = 1; v < ndev && P->rc.load() == MAG_OK; v++) {
-    const int victim = (d + v) % ndev;
-    if (P->devices[victim] == P->devices[d]) continue;   // same GPU listed twice: its own threads finish that share
-    if (victim >= J.nchunks) continue;
-    const int last = victim + ((J.nchunks - 1 - victim) / ndev) * ndev;
-    for (int k = last; k >= 0 && P->rc.load() == MAG_OK; k -= ndev)
-      if (try_claim(k) && !one(k, true)) return;
+  // 2. steal from the tails of the other devices' shares -- but only from a device whose threads are ALL inside a
+  // chunk: an unclaimed chunk of a device with a free thread is about to be taken by its owner (at start-up every
+  // share is unclaimed; a thread that loses the race for its own device's only chunk must not grab the neighbour's)
+  while (P->unclaimed.load() > 0 && P->rc.load() == MAG_OK) {
+    bool took = false;
+    for (int v = 1; v < ndev && !took; v++) {
+      const int victim = (d + v) % ndev;
+      if (victim >= J.nchunks) continue;
+      const bool same_gpu = P->devices[victim] == P->devices[d];   // a GPU listed twice: its threads share the work freely
+      if (!same_gpu && P->active[victim].load() < P->per_dev) continue;
+      const int last = victim + ((J.nchunks - 1 - victim) / ndev) * ndev;
+      for (int k = last; k >= 0 && !took; k -= ndev)
+        if (try_claim(k)) { took = true; if (!one(k, true)) return; }
+    }
+    if (!took) std::this_thread::sleep_for(std::chrono::microseconds(200));
   }
-  // 3. (a device listed more than once shares one GPU: help with whatever is left)
-  for (int k = J.nchunks - 1; k >= 0 && P->rc.load() == MAG_OK; k--)
-    if (try_claim(k) && !one(k, k % ndev != d)) return;
 }
 
 void worker_main(mag_partition* P, int wi) {
@@ -175,8 +189,9 @@ int run_partition(mag_partition* P, int32_t* chunks_done, int32_t* chunks_stolen
   J.nchunks = (J.ngal + J.chunk - 1) / J.chunk;
   J.claimed.reset(new std::atomic<int>[J.nchunks]);
   for (int k = 0; k < J.nchunks; k++) J.claimed[k].store(0);
+  P->unclaimed.store(J.nchunks);
   P->rc.store(MAG_OK);
-  for (int d = 0; d < P->ndev; d++) { P->done[d].store(0); P->stolen[d].store(0); P->launches[d].store(0); P->busy_us[d].store(0); }
+  for (int d = 0; d < P->ndev; d++) { P->done[d].store(0); P->stolen[d].store(0); P->active[d].store(0); P->launches[d].store(0); P->busy_us[d].store(0); }
   {
     std::lock_guard<std::mutex> lk(P->mu);
     P->err.clear();

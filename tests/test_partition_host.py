@@ -91,6 +91,25 @@ def test_static_share_and_stealing(stub_solver):
         part.close()
 
 
+def test_no_stealing_from_a_device_with_a_free_thread(stub_solver):
+    """One chunk per device (the automatic chunk size of a strong-scaling run): the thread that loses the race for
+    its own device's only chunk must not take the neighbour's before the neighbour's threads have started
+    (round 2, first 8-GPU run: chunks done [2, 1, 0, 1, 0, 1, 1, 2])."""
+    S = stub_solver
+    for ndev in (2, 4, 8):
+        ids, t, inp = catalogue(ndev * 40)
+        part = S.Partition(list(range(ndev)))
+        try:
+            for _ in range(5):
+                r = part.solve(ids, t, inp, chunk=40, profiles=PROF, scalars=SCAL)
+                assert r["chunks_done"].tolist() == [1] * ndev and r["chunks_stolen"].tolist() == [0] * ndev
+                assert sorted(set(r["flags"].tolist())) == list(range(ndev))      # every device solved its own chunk
+                r = part.solve(ids, t, inp, chunk=20, profiles=PROF, scalars=SCAL)      # two chunks per device, two threads each
+                assert r["chunks_done"].tolist() == [2] * ndev and r["chunks_stolen"].tolist() == [0] * ndev
+        finally:
+            part.close()
+
+
 def test_automatic_chunk_size(stub_solver):
     S = stub_solver
     ids, t, inp = catalogue(5000, nz=2)

@@ -27,7 +27,7 @@ for chunk in (100, 250):
 part.close()
 PY
 echo "partition check rc=$?"; cat gpurun_out/r2_part8_check.log | tail -4
-for N in 8 4 2; do
+for N in 8 4; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29510 + N)) \
       bench.py --gpus $N --steps 3 --warmup 2 > gpurun_out/r2_bench_n$N.log 2>&1
   echo "bench N=$N rc=$?" | tee -a gpurun_out/r2_bench_n$N.log
