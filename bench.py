@@ -267,7 +267,10 @@ def run_b200(args):
     assert int(r_e2e["point_stages"].sum()) == W_total, "e2e and HBM-resident arms disagree"
 
     # ---- roofline of the evolve kernels: one context, one stream, CUDA events (GPU 0, one chunk of the partition)
+    # (the partition's contexts are released first: each holds a snapshot-record arena for its chunk, and a third one
+    #  beside them would not fit a whole chunk and run it as two sub-launches)
     Gs = min(G, int(pstats["chunk"]))
+    part.close()
     solver = DynamoSolver(device=0)
     with torch.cuda.device(devs[0]):
         r0 = res[0]
@@ -287,6 +290,7 @@ def run_b200(args):
         W_slice = int(r0["ps"][:Gs].sum().item())
         snaps_slice = int((r0["status"][:Gs] != ord("-")).sum().item())     # galaxy-snapshots the launch processed
         info = solver.info()
+        assert info["records_chunk"] >= Gs, f"roofline leg ran as sub-launches of {info['records_chunk']} galaxies, not one launch of {Gs}"
         fp64_peak = solver.measure_fp64_peak(5)
     ms_evolve = tim["ms_kernels"] - tim["ms_profile_phase"]
 

@@ -911,9 +911,10 @@ int mag_test_rng(int32_t igal, int32_t seed, int32_t kind, int32_t n, double* ou
   cudaFree(d);
   return MAG_OK;
 }
-int mag_ctx_info(mag_ctx_t* c, int32_t* out /* [12]: sm_count, profile CTAs/SM, profile warps, nxcap, use_fast, fast-path replays and
+int mag_ctx_info(mag_ctx_t* c, int32_t* out /* [16]: sm_count, profile CTAs/SM, profile warps, nxcap, use_fast, fast-path replays and
                                                heavy-class galaxies of the last solve (last chunk), one-warp teams/SM, one-warp teams,
-                                               four-warp teams/SM, four-warp teams, heavy mode */) {
+                                               four-warp teams/SM, four-warp teams, heavy mode, galaxies the snapshot-record arena
+                                               holds (a larger call runs as several sub-launches), 3 spare */) {
   if (!c) return MAG_ERR_BAD_ARGUMENT;
   out[0] = c->sm_count; out[1] = c->ctasA_per_sm; out[2] = c->nwarpsA; out[3] = c->nxcap; out[4] = c->use_fast;
   out[5] = 0; out[6] = 0;
@@ -921,6 +922,7 @@ int mag_ctx_info(mag_ctx_t* c, int32_t* out /* [12]: sm_count, profile CTAs/SM, 
   cudaMemcpy(&out[5], c->d_counter + CNT_REPLAYS, sizeof(int), cudaMemcpyDeviceToHost);
   cudaMemcpy(&out[6], c->d_counter + CNT_NHEAVY_SUM, sizeof(int), cudaMemcpyDeviceToHost);
   out[7] = c->ctasB_per_sm; out[8] = c->nteamsB; out[9] = c->ctasH_per_sm; out[10] = c->nteamsH; out[11] = c->policy.mode;
+  out[12] = c->chunk_cap; out[13] = out[14] = out[15] = 0;
   return MAG_OK;
 }
 int mag_set_fast_path(mag_ctx_t* c, int32_t on) {

@@ -35,8 +35,11 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -155,46 +158,124 @@ class Hdf5Writer {
     const size_t rank = d.dims.size();
     const uint64_t nlast = rank == 1 ? 1 : d.dims[rank - 1];
     const uint64_t mid = rank == 3 ? d.dims[1] : 1;
-    const uint64_t celems = d.cs * mid;
-    std::vector<std::string> enc((size_t)nlast);
-    auto build = [&](uint64_t il) {
-      std::vector<char> raw((size_t)(celems * es));
+    std::vector<ChunkJob> jobs((size_t)nlast);
+    for (uint64_t il = 0; il < nlast; il++) {
+      jobs[(size_t)il].h = h; jobs[(size_t)il].kb = kb; jobs[(size_t)il].il = il;
+      jobs[(size_t)il].fill = [=](char* raw, uint64_t) {
+        const char* src = (const char*)data;
+        for (uint64_t g = 0; g < nb; g++)
+          for (uint64_t i = 0; i < mid; i++)
+            std::memcpy(raw + (g * mid + i) * es, src + ((g * mid + i) * nlast + il) * es, (size_t)es);
+      };
+    }
+    write_chunks(jobs);
+  }
+
+  // One chunk of a chunked dataset: block kb (galaxies [kb*cs, ...)), index `il` of the last dimension.
+  // `fill` receives the chunk's buffer -- [cs][dims[1]] elements for a rank-3 dataset, [cs] otherwise --
+  // already holding the fill value, and the number of galaxies of the block that exist; it stores the
+  // rows it has.  Called on a worker thread.
+  struct ChunkJob {
+    int h = -1;
+    uint64_t kb = 0, il = 0;
+    std::function<void(char* raw, uint64_t nb)> fill;
+  };
+  // Builds (fill + deflate) the chunks on the writer's threads and appends them in the order of `jobs`;
+  // at most a window of encoded chunks is held in memory.  Writing a chunk again replaces it.
+  void write_chunks(const std::vector<ChunkJob>& jobs) {
+    if (!opt_.chunking) throw std::runtime_error("write_chunks needs a chunked file");
+    const size_t n = jobs.size();
+    if (n == 0) return;
+    uint64_t raw_total = 0;
+    for (const ChunkJob& j : jobs) {
+      if (j.h < 0 || j.h >= (int)dsets_.size()) throw std::runtime_error("bad dataset handle");
+      const Dset& d = dsets_[j.h];
+      const uint64_t nlast = d.dims.size() == 1 ? 1 : d.dims.back();
+      if (j.kb * d.cs >= d.dims[0] || j.il >= nlast) throw std::runtime_error("chunk out of range: " + d.name);
+      raw_total += d.cs * (d.dims.size() == 3 ? d.dims[1] : 1) * elem_size(d.type);
+    }
+    auto encode = [&](const ChunkJob& j, std::vector<char>& raw, std::string& out) {
+      const Dset& d = dsets_[j.h];
+      const uint64_t es = elem_size(d.type), celems = d.cs * (d.dims.size() == 3 ? d.dims[1] : 1);
+      raw.resize((size_t)(celems * es));
       fill_buffer(d, raw.data(), celems);   // rows of an edge chunk beyond the last galaxy hold the fill value
-      const char* src = (const char*)data;
-      for (uint64_t g = 0; g < nb; g++)
-        for (uint64_t i = 0; i < mid; i++)
-          std::memcpy(&raw[(size_t)((g * mid + i) * es)], src + ((g * mid + i) * nlast + il) * es, (size_t)es);
+      j.fill(raw.data(), std::min<uint64_t>(d.cs, d.dims[0] - j.kb * d.cs));
       if (opt_.compression) {
         uLongf cap = compressBound((uLong)raw.size());
-        std::string z((size_t)cap, '\0');
-        if (compress2((Bytef*)&z[0], &cap, (const Bytef*)raw.data(), (uLong)raw.size(), opt_.level) != Z_OK) throw std::runtime_error("deflate failed");
-        z.resize((size_t)cap);
-        enc[(size_t)il].swap(z);
+        out.assign((size_t)cap, '\0');
+        if (compress2((Bytef*)&out[0], &cap, (const Bytef*)raw.data(), (uLong)raw.size(), opt_.level) != Z_OK) throw std::runtime_error("deflate failed");
+        out.resize((size_t)cap);
       } else {
-        enc[(size_t)il].assign(raw.data(), raw.size());
+        out.assign(raw.data(), raw.size());
       }
     };
-    int nt = opt_.threads > 0 ? opt_.threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
-    if ((uint64_t)nt > nlast) nt = (int)nlast;
-    if (nt <= 1 || !opt_.compression) {
-      for (uint64_t il = 0; il < nlast; il++) build(il);
-    } else {
-      std::vector<std::thread> th;
-      std::string err;
-      for (int k = 0; k < nt; k++)
-        th.emplace_back([&, k] { try { for (uint64_t il = (uint64_t)k; il < nlast; il += (uint64_t)nt) build(il); } catch (const std::exception& e) { err = e.what(); } });
-      for (auto& t : th) t.join();
-      if (!err.empty()) throw std::runtime_error(err);
-    }
-    for (uint64_t il = 0; il < nlast; il++) {
+    auto append = [&](const ChunkJob& j, const std::string& z) {
+      Dset& d = dsets_[j.h];
+      const size_t rank = d.dims.size();
       H5ChunkRec r;
       r.offs.assign(rank, 0);
-      r.offs[0] = g0;
-      if (rank >= 2) r.offs[rank - 1] = il;
-      r.addr = pos_; r.size = (uint32_t)enc[(size_t)il].size(); r.mask = 0;
-      put_raw(enc[(size_t)il].data(), enc[(size_t)il].size());
+      r.offs[0] = j.kb * d.cs;
+      if (rank >= 2) r.offs[rank - 1] = j.il;
+      r.addr = pos_; r.size = (uint32_t)z.size(); r.mask = 0;
+      put_raw(z.data(), z.size());
       d.chunks[r.offs] = r;
+    };
+    int nt = opt_.threads > 0 ? opt_.threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    if ((size_t)nt > n) nt = (int)n;
+    if (nt <= 1 || raw_total < (1u << 20)) {          // small: not worth a thread
+      std::vector<char> raw; std::string z;
+      for (const ChunkJob& j : jobs) { encode(j, raw, z); append(j, z); }
+      return;
     }
+    std::vector<std::string> enc(n);
+    std::vector<char> ready(n, 0);
+    std::mutex mu;
+    std::condition_variable cv_ready, cv_room;
+    size_t next = 0, written = 0;
+    const size_t window = 4 * (size_t)nt;
+    std::string err;
+    auto worker = [&] {
+      std::vector<char> raw;
+      for (;;) {
+        size_t i;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv_room.wait(lk, [&] { return next >= n || next < written + window || !err.empty(); });
+          if (next >= n || !err.empty()) return;
+          i = next++;
+        }
+        std::string e;
+        try { encode(jobs[i], raw, enc[i]); } catch (const std::exception& ex) { e = ex.what(); if (e.empty()) e = "chunk encoding failed"; }
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          if (!e.empty() && err.empty()) err = e;
+          ready[i] = 1;
+        }
+        cv_ready.notify_all();
+        if (!e.empty()) { cv_room.notify_all(); return; }
+      }
+    };
+    std::vector<std::thread> th;
+    for (int k = 0; k < nt; k++) th.emplace_back(worker);
+    std::string werr;
+    for (size_t i = 0; i < n; i++) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_ready.wait(lk, [&] { return ready[i] || !err.empty(); });
+        if (!err.empty()) break;
+      }
+      try { append(jobs[i], enc[i]); } catch (const std::exception& ex) { werr = ex.what(); }
+      std::string().swap(enc[i]);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        written = i + 1;
+        if (!werr.empty() && err.empty()) err = werr;
+      }
+      cv_room.notify_all();
+      if (!werr.empty()) break;
+    }
+    for (auto& t : th) t.join();
+    if (!err.empty()) throw std::runtime_error(err);
   }
 
   void add_root_attribute(const std::string& name, const std::string& text) {

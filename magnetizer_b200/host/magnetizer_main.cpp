@@ -22,16 +22,20 @@
 // flag is set are skipped (IO_start_galaxy, IO_hdf5.f90:244-266).
 //
 //   Magnetizer_b200 <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.hdf5]
-//                   [--restart] [--stop-after N] [--dry-run] [--raw-input file]
+//                   [--restart] [--stop-after N] [--dry-run] [--raw-input file] [--no-overlap]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include <cuda_runtime.h>
 
@@ -182,7 +186,7 @@ double seconds_since(const std::chrono::steady_clock::time_point& t0) {
 int main(int argc, char** argv) {
   if (argc < 2) {
     std::fprintf(stderr, "usage: %s <parameters.in> [gal_id ...] [--devices 0,1,...] [--chunk N] [--out file.hdf5]\n"
-                         "          [--restart] [--stop-after N] [--dry-run] [--raw-input file]\n", argv[0]);
+                         "          [--restart] [--stop-after N] [--dry-run] [--raw-input file] [--no-overlap]\n", argv[0]);
     return 2;
   }
   try {
@@ -192,12 +196,13 @@ int main(int argc, char** argv) {
     std::vector<int32_t> list, devices;
     int chunk = 0;
     std::string out_path, raw_input;
-    bool dry_run = false, restart = false;
+    bool dry_run = false, restart = false, overlap = true;
     long stop_after = -1;
     for (int i = 2; i < argc; i++) {
       const std::string a = argv[i];
       if (a == "--dry-run") { dry_run = true; continue; }
       if (a == "--restart") { restart = true; continue; }
+      if (a == "--no-overlap") { overlap = false; continue; }
       if (a == "--stop-after" && i + 1 < argc) { stop_after = std::atol(argv[++i]); continue; }
       if (a == "--raw-input" && i + 1 < argc) { raw_input = argv[++i]; continue; }
       if (a == "--devices" && i + 1 < argc) {
@@ -321,56 +326,49 @@ int main(int argc, char** argv) {
     // p_ncheckpoint galaxies are to be solved; solve, write, flush; then look for the STOP file / the walltime
     std::vector<char> is_todo(ngals, 0);
     for (int g : todo) is_todo[g] = 1;
-    HostBuf b_in, b_prof, b_scal, b_stat, b_nsteps, b_err, b_ps, b_flags;
+    // The results of a cycle are written (unit conversion, deflate, flush) by a writer thread while the next cycle is
+    // packed and solved: two sets of page-locked buffers, unless --no-overlap or two sets would not fit the host memory.
+    struct Cycle {
+      HostBuf b_in, b_prof, b_scal, b_stat, b_nsteps, b_err, b_ps, b_flags;
+      std::vector<int> sel;            // catalogue indices solved in this cycle, ascending
+      size_t kb0 = 0, kb1 = 0, solved_after = 0;
+      double cyc_s = 0;
+      long long cyc_stages = 0;
+    } cyc[2];
     std::vector<int32_t> done((size_t)devices.size()), stolen((size_t)devices.size()), done_tot(devices.size(), 0), stolen_tot(devices.size(), 0);
     std::map<char, long> counts;
-    double solve_s = 0, write_s = 0;
+    double solve_s = 0, write_s = 0, stage_s = 0, wait_s = 0;
+    const double setup_s = seconds_since(t_start);   // namelist, input file, output file, contexts
     long long total_stages = 0;
     size_t solved = 0, cycles = 0;
     bool stopped = false;
     const size_t ncheck = (size_t)std::max(1, cfg.p_ncheckpoint);
-    for (size_t kb0 = 0; kb0 < nblocks && !stopped;) {
-      std::vector<int> sel;            // catalogue indices to solve in this cycle, ascending
-      size_t kb1 = kb0;
-      while (kb1 < nblocks && sel.size() < ncheck) {
-        for (size_t g = kb1 * cs; g < std::min((kb1 + 1) * cs, (size_t)ngals); g++) if (is_todo[g]) sel.push_back((int)g);
-        kb1++;
+    {
+      const double cycle_bytes = (double)std::min(ncheck + cs, todo.size()) * nz * (8.0 * (13 + pq.size() * (double)nr + sq.size()) + 1.0);
+      const double host_bytes = (double)sysconf(_SC_PHYS_PAGES) * (double)sysconf(_SC_PAGESIZE);
+      if (overlap && 2.0 * cycle_bytes > 0.4 * host_bytes) {
+        overlap = false;
+        if (cfg.info > 0) std::printf("  (two result sets of %.1f GB do not fit the host memory: cycles are written before the next one is solved)\n", cycle_bytes / 1e9);
       }
-      if (sel.empty()) { kb0 = kb1; continue; }
+    }
+
+    // -- write_output (output.f90:23-236): unit conversion, (ngals, nx, nz) layout, Log group; block by block
+    auto write_cycle = [&](const Cycle& C) {
+      const std::vector<int>& sel = C.sel;
       const int nsel = (int)sel.size();
-      // -- solve the cycle's galaxies: packed inputs in, packed results out (page-locked: the kernels store into them)
-      b_in.ensure(sizeof(double) * 13 * nsel * nz);
-      b_prof.ensure(sizeof(double) * pq.size() * nsel * nz * nr); b_scal.ensure(sizeof(double) * std::max<size_t>(1, sq.size()) * nsel * nz);
-      b_stat.ensure((size_t)nsel * nz); b_nsteps.ensure(4 * (size_t)nsel); b_err.ensure(4 * (size_t)nsel); b_ps.ensure(8 * (size_t)nsel); b_flags.ensure(4 * (size_t)nsel);
-      double* sin = (double*)b_in.p;
-      std::vector<int32_t> sel_ids(nsel);
-      for (int k = 0; k < nsel; k++) sel_ids[k] = sel[k] + 1;
-      for (int c = 0; c < 13; c++)
-        for (int k = 0; k < nsel; k++)
-          std::memcpy(&sin[((size_t)c * nsel + k) * nz], &in.inputs[((size_t)c * ngals + sel[k]) * nz], sizeof(double) * nz);
-      const double* profiles = (const double*)b_prof.p;
-      const double* scalars = (const double*)b_scal.p;
-      const char* status = (const char*)b_stat.p;
-      const int32_t *nsteps = (const int32_t*)b_nsteps.p, *error = (const int32_t*)b_err.p;
-      const int64_t* stages = (const int64_t*)b_ps.p;
-      mag_outputs_t out{(double*)b_prof.p, sq.empty() ? nullptr : (double*)b_scal.p, (char*)b_stat.p, (int32_t*)b_nsteps.p, (int32_t*)b_err.p,
-                        (int64_t*)b_ps.p, (uint32_t*)b_flags.p};
-      const auto t0 = std::chrono::steady_clock::now();
-      const int rc = mag_partition_solve(part, nsel, sel_ids.data(), nz, in.t_gyr.data(), sin, (int)pq.size(), pq.data(), (int)sq.size(), sq.data(),
-                                         &out, chunk, done.data(), stolen.data());
-      if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
-      const double cyc_s = seconds_since(t0);
-      solve_s += cyc_s;
-      long long cyc_stages = 0;
-      for (int k = 0; k < nsel; k++) cyc_stages += stages[k];
-      total_stages += cyc_stages;
-      for (size_t d = 0; d < devices.size(); d++) { done_tot[d] += done[d]; stolen_tot[d] += stolen[d]; }
-      // -- write_output (output.f90:23-236): unit conversion, (ngals, nx, nz) layout, Log group; block by block
+      const double* profiles = (const double*)C.b_prof.p;
+      const double* scalars = (const double*)C.b_scal.p;
+      const char* status = (const char*)C.b_stat.p;
+      const int32_t *nsteps = (const int32_t*)C.b_nsteps.p, *error = (const int32_t*)C.b_err.p;
+      const int64_t* stages = (const int64_t*)C.b_ps.p;
+      const double cyc_s = C.cyc_s;
+      const long long cyc_stages = C.cyc_stages;
       const auto t1 = std::chrono::steady_clock::now();
-      std::vector<double> blk3(cs * (size_t)nr * nz), blk2(cs * (size_t)nz), blk1(cs);
+      std::vector<double> blk3, blk2(cs * (size_t)nz), blk1(cs);
       std::vector<char> blkc(cs * (size_t)nz);
+      std::vector<maghost::Hdf5Writer::ChunkJob> jobs;   // profile chunks of the whole cycle
       size_t k_lo = 0;
-      for (size_t kb = kb0; kb < kb1; kb++) {
+      for (size_t kb = C.kb0; kb < C.kb1; kb++) {
         const size_t g0 = kb * cs, nb = std::min(cs, (size_t)ngals - g0);
         size_t k_hi = k_lo;
         while (k_hi < (size_t)nsel && (size_t)sel[k_hi] < g0 + nb) k_hi++;
@@ -378,6 +376,7 @@ int main(int argc, char** argv) {
         bool merge = false;                                           // rows an earlier invocation completed are kept
         for (size_t g = g0; g < g0 + nb; g++) if (completed[g]) merge = true;
         auto base3 = [&](const std::string& path) {
+          blk3.resize(cs * (size_t)nr * nz);
           if (merge && prev && prev->exists(path)) { const maghost::H5Reader::Data d = prev->read_rows(path, g0, nb); std::copy(d.v.begin(), d.v.end(), blk3.begin()); }
           else std::fill(blk3.begin(), blk3.begin() + nb * (size_t)nr * nz, maghost::Hdf5Writer::kFill);
         };
@@ -389,6 +388,26 @@ int main(int argc, char** argv) {
           const std::string name = kProfileNames[pq[q]];
           const double fac = unit_factor(name);
           const double* src = profiles + q * (size_t)nsel * nz * nr;
+          if (wopt.chunking && !merge) {
+            // a chunk holds all radii of ONE snapshot of the block's galaxies (IO_hdf5.f90:940-952), and the solver's rows are
+            // [galaxy][snapshot][radius]: every chunk is filled from contiguous rows, on the writer's threads
+            const int* selp = sel.data();
+            for (int iz = 0; iz < nz; iz++) {
+              maghost::Hdf5Writer::ChunkJob job;
+              job.kb = kb; job.il = (uint64_t)iz;
+              job.fill = [=](char* raw, uint64_t) {
+                double* dst = (double*)raw;
+                for (size_t k = k_lo; k < k_hi; k++) {
+                  const double* row = src + (k * nz + iz) * nr;
+                  double* o = dst + ((size_t)selp[k] - g0) * nr;
+                  for (int i = 0; i < nr; i++) o[i] = (row[i] == MAG_INVALID) ? row[i] : row[i] * fac;
+                }
+              };
+              if (prof_cols[q].h >= 0) { job.h = prof_cols[q].h; jobs.push_back(job); }
+              if (name == "rkpc") { job.h = h_r; jobs.push_back(job); }
+            }
+            continue;
+          }
           base3(name == "rkpc" && !have_rkpc ? "Output/r" : "Output/" + name);
           for (size_t k = k_lo; k < k_hi; k++) {
             double* dst = &blk3[((size_t)sel[k] - g0) * nr * nz];
@@ -426,22 +445,82 @@ int main(int argc, char** argv) {
         w.write_block(h_runtime, kb, blk1.data());
         k_lo = k_hi;
       }
+      if (!jobs.empty()) w.write_chunks(jobs);
       w.flush();                                                      // IO_flush every checkpoint cycle (distributor.f90:336)
-      write_s += seconds_since(t1);
-      solved += (size_t)nsel;
+      const double ws = seconds_since(t1);
+      write_s += ws;
       cycles++;
-      if (cfg.info > 1) std::printf("  cycle %zu: %d galaxies solved in %.3f s, flushed (%zu of %zu done)\n", cycles, nsel, cyc_s, solved, todo.size());
+      if (cfg.info > 1) std::printf("  cycle %zu: %d galaxies solved in %.3f s, written and flushed in %.3f s (%zu of %zu done)\n", cycles, nsel, cyc_s, ws, C.solved_after, todo.size());
+    };
+    std::thread writer;
+    std::exception_ptr writer_error;
+    auto join_writer = [&] {
+      if (!writer.joinable()) return;
+      const auto tw = std::chrono::steady_clock::now();
+      writer.join();
+      wait_s += seconds_since(tw);
+      if (writer_error) std::rethrow_exception(writer_error);
+    };
+    struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } join_guard{writer};   // an exception on the solve side
+
+    int cur = 0;
+    for (size_t kb0 = 0; kb0 < nblocks && !stopped;) {
+      Cycle& C = cyc[cur];             // its previous results (two cycles ago) are on disk: the writer of the last cycle started after that join
+      std::vector<int>& sel = C.sel;
+      sel.clear();
+      size_t kb1 = kb0;
+      while (kb1 < nblocks && sel.size() < ncheck) {
+        for (size_t g = kb1 * cs; g < std::min((kb1 + 1) * cs, (size_t)ngals); g++) if (is_todo[g]) sel.push_back((int)g);
+        kb1++;
+      }
+      if (sel.empty()) { kb0 = kb1; continue; }
+      const int nsel = (int)sel.size();
+      // -- solve the cycle's galaxies: packed inputs in, packed results out (page-locked: the kernels store into them)
+      const auto ts = std::chrono::steady_clock::now();
+      C.b_in.ensure(sizeof(double) * 13 * nsel * nz);
+      C.b_prof.ensure(sizeof(double) * pq.size() * nsel * nz * nr); C.b_scal.ensure(sizeof(double) * std::max<size_t>(1, sq.size()) * nsel * nz);
+      C.b_stat.ensure((size_t)nsel * nz); C.b_nsteps.ensure(4 * (size_t)nsel); C.b_err.ensure(4 * (size_t)nsel); C.b_ps.ensure(8 * (size_t)nsel); C.b_flags.ensure(4 * (size_t)nsel);
+      double* sin = (double*)C.b_in.p;
+      std::vector<int32_t> sel_ids(nsel);
+      for (int k = 0; k < nsel; k++) sel_ids[k] = sel[k] + 1;
+      for (int c = 0; c < 13; c++)
+        for (int k = 0; k < nsel; k++)
+          std::memcpy(&sin[((size_t)c * nsel + k) * nz], &in.inputs[((size_t)c * ngals + sel[k]) * nz], sizeof(double) * nz);
+      mag_outputs_t out{(double*)C.b_prof.p, sq.empty() ? nullptr : (double*)C.b_scal.p, (char*)C.b_stat.p, (int32_t*)C.b_nsteps.p, (int32_t*)C.b_err.p,
+                        (int64_t*)C.b_ps.p, (uint32_t*)C.b_flags.p};
+      stage_s += seconds_since(ts);
+      const auto t0 = std::chrono::steady_clock::now();
+      const int rc = mag_partition_solve(part, nsel, sel_ids.data(), nz, in.t_gyr.data(), sin, (int)pq.size(), pq.data(), (int)sq.size(), sq.data(),
+                                         &out, chunk, done.data(), stolen.data());
+      if (rc != MAG_OK) throw std::runtime_error(std::string("solve failed (") + std::to_string(rc) + "): " + mag_partition_last_error());
+      C.cyc_s = seconds_since(t0);
+      solve_s += C.cyc_s;
+      C.cyc_stages = 0;
+      const int64_t* stages = (const int64_t*)C.b_ps.p;
+      for (int k = 0; k < nsel; k++) C.cyc_stages += stages[k];
+      total_stages += C.cyc_stages;
+      for (size_t d = 0; d < devices.size(); d++) { done_tot[d] += done[d]; stolen_tot[d] += stolen[d]; }
+      solved += (size_t)nsel;
+      C.kb0 = kb0; C.kb1 = kb1; C.solved_after = solved;
+      join_writer();                   // the previous cycle is on disk
+      writer = std::thread([&, pc = &C] { try { write_cycle(*pc); } catch (...) { writer_error = std::current_exception(); } });
+      if (!overlap) join_writer();
+      else cur ^= 1;
       kb0 = kb1;
       // graceful stop (distributor.f90:299-312): a file named STOP in the working directory, or the walltime
       if (FILE* sf = std::fopen("STOP", "rb")) { std::fclose(sf); stopped = true; std::printf("  STOP file found: exiting after this cycle\n"); }
       if (cfg.p_max_walltime > 0 && seconds_since(t_start) > cfg.p_max_walltime) { stopped = true; std::printf("  p_max_walltime reached: exiting after this cycle\n"); }
     }
+    join_writer();
     w.close();
     prev.reset();
     mag_partition_destroy(part);
     std::printf("  solved %zu galaxies in %.3f s  (%.1f galaxies/s, %.3e point-stages/s); output written in %.3f s (%.1f MB, %zu flush(es))\n",
                 solved, solve_s, solve_s > 0 ? solved / solve_s : 0.0, solve_s > 0 ? total_stages / solve_s : 0.0, write_s,
                 (double)w.bytes_written() / 1e6, cycles);
+    std::printf("  wall %.3f s: setup (namelist, input, contexts) %.3f, page-locked buffers + input packing %.3f, solve %.3f, write_output + flush %.3f "
+                "(%s; the solve side waited %.3f s for the writer)\n",
+                seconds_since(t_start), setup_s, stage_s, solve_s, write_s, overlap ? "on a writer thread beside the next cycle's solve" : "between the solves", wait_s);
     for (size_t d = 0; d < devices.size(); d++)
       std::printf("  GPU %d: %d chunks (%d stolen)\n", devices[d], done_tot[d], stolen_tot[d]);
     std::printf("  status codes:");

@@ -92,11 +92,11 @@ class DynamoSolver:
 
     # -- diagnostics ---------------------------------------------------------
     def info(self):
-        out = (C.c_int32 * 12)()
+        out = (C.c_int32 * 16)()
         _check(self._lib.mag_ctx_info(self._ctx, out), "mag_ctx_info")
         return dict(sm_count=out[0], profile_ctas_per_sm=out[1], profile_warps=out[2], nxcap=out[3], use_fast=out[4],
                     fast_path_replays=out[5], heavy_galaxies=out[6], evolve_teams_per_sm=out[7], evolve_teams=out[8],
-                    heavy_teams_per_sm=out[9], heavy_teams=out[10], heavy_mode=out[11])
+                    heavy_teams_per_sm=out[9], heavy_teams=out[10], heavy_mode=out[11], records_chunk=out[12])
 
     def set_fast_path(self, on: bool):
         _check(self._lib.mag_set_fast_path(self._ctx, C.c_int32(1 if on else 0)), "mag_set_fast_path")
