@@ -57,6 +57,24 @@ namespace magdev {
 #ifndef MAG_WARP_UNROLL_MAXPPL
 #define MAG_WARP_UNROLL_MAXPPL 0
 #endif
+#ifndef MAG_WARP_UNROLL_JM
+#define MAG_WARP_UNROLL_JM 0      // 1: the instantiations with a compile-time outer alignment unroll their three stages
+#endif
+#ifndef MAG_WARP_DUE_AHEAD
+#define MAG_WARP_DUE_AHEAD 0     // the step of the next floor-sign refresh is found ahead of the steps of a block
+#endif
+#ifndef MAG_WARP_OPAQUE_ADDR
+#define MAG_WARP_OPAQUE_ADDR 0   // shared addresses of the pair table / stage constants kept in registers (no S2UR + ULEA per stage)
+#endif
+#ifndef MAG_WARP_STAGE_LOOP2
+#define MAG_WARP_STAGE_LOOP2 0   // the stage loop stops once for save_alp() instead of testing for it in every stage
+#endif
+#ifndef MAG_WARP_GHOST_SELECT
+#define MAG_WARP_GHOST_SELECT 0  // outer ghosts of grids that fill their last lane: selects, no branch
+#endif
+#ifndef MAG_WARP_ALIGNED4
+#define MAG_WARP_ALIGNED4 0       // own instantiation of the four-register loop for grids that fill their last lane (nx = 107: 90 % of its stages)
+#endif
 #define WM_REGS 0
 #define WM_WSM 1
 #define WM_WSM2 2
@@ -166,6 +184,9 @@ __device__ __forceinline__ void outer_ghosts(WarpState<PPL, MODE>& S, const int 
 // up to this PPL the stage applies the ghost entries after its phase 0; the large-grid variants
 // apply them right after the exchange (fewer values live across the stage: no spills)
 #define WARP_LATE_GHOSTS_MAXPPL 6
+#ifndef WARP_T_IN_STAGE_MAXPPL
+#define WARP_T_IN_STAGE_MAXPPL 0
+#endif
 // 64-bit shuffles as two explicit 32-bit ones (the compiler's own lowering of a double shuffle
 // lands the halves in swapped registers and then swaps them back with three LOP3 each)
 __device__ __forceinline__ double shfl_down1(double x) {
@@ -202,10 +223,12 @@ __device__ __forceinline__ void warp_ghosts(WarpState<PPL, MODE>& S, const int l
   // outer end
   if (JM >= 0) {
     outer_ghosts<PPL, MODE, (JM >= 0 ? JM : 0)>(S, lane, tm);
-  } else if (jm == PPL - 1) {   // the default grid (nx = 107) and every other grid that fills its last lane
+  } else if (!MAG_WARP_GHOST_SELECT && jm == PPL - 1) {   // the default grid (nx = 107) and every other grid that fills its last lane
     outer_ghosts<PPL, MODE, PPL - 1>(S, lane, tm);
   } else {
-    switch (jm) {
+    // the default grid (nx = 107) and every other grid that fills its last lane: selects only, no branch (90 % of the stages)
+    if (MAG_WARP_GHOST_SELECT) mirror_ghosts<PPL, MODE, 3 + PPL - 1>(S, lane == tm && jm == PPL - 1, true);
+    if (!MAG_WARP_GHOST_SELECT || __builtin_expect(jm != PPL - 1, 0)) switch (jm) {
       case 0: outer_ghosts<PPL, MODE, 0>(S, lane, tm); break;
       case 1: outer_ghosts<PPL, MODE, 1>(S, lane, tm); break;
       case 2: outer_ghosts<PPL, MODE, 2>(S, lane, tm); break;
@@ -390,7 +413,12 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
   const int g0 = lane * PPL - WARP_J0 + MAG_NGHOST;   // grid index of register 0 (slot s holds p = s - WARP_J0, g = p + 3)
   double2* const wt2 = reinterpret_cast<double2*>(rs->pool) + lane;                          // shared pair table, this lane's column
   double2* const tab = reinterpret_cast<double2*>(W + (size_t)WARP_TABLE_ARRAY * nxcap) + lane;   // global pair table
-  const unsigned wsa = (unsigned)__cvta_generic_to_shared(rs->pool) + 16u * lane;
+  // 32-bit shared addresses of this lane's column of the pair table and of the stage constants.  They pass through an
+  // empty asm so that the compiler keeps them in a register: it would otherwise rebuild the shared window base in every
+  // stage (S2UR SR_CgaCtaId + ULEA: a 20-cycle special-register read in front of the first loads, 3 % of the stall samples).
+  unsigned wsa = (unsigned)__cvta_generic_to_shared(rs->pool) + 16u * lane;
+  unsigned sdg = (unsigned)__cvta_generic_to_shared(&rs->stage_dg[0]);
+  if (MAG_WARP_OPAQUE_ADDR) asm volatile("" : "+r"(wsa), "+r"(sdg));
 
   PHASE_BEGIN;
   prepare_fast_coefs(G, nx);
@@ -509,13 +537,24 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
       mAs = (unsigned)max((int)mAs, __double2hiint(S.f[2][j]));
       mAu = max(mAu, (unsigned)__double2hiint(S.f[2][j]));
     }
+    // The step at which the floor signs are redrawn next (this_t - t_last > tmk) is found ahead of the steps, `nb`
+    // independent evaluations of the step's own expression, so that the steps do not start with that serial chain
+    // (I2F, DMUL, DADD, DADD, DSETP, BRA: 2.4 % of the stall samples).
+    auto first_due = [&](const int s0) {
+      int r = nb;
+#pragma unroll 4
+      for (int s = nb - 1; s >= s0; s--)
+        if ((t_Gyr + dtg * (double)(jt + s)) - t_last > tmk) r = s;
+      return r;
+    };
+    int s_evt = !MAG_WARP_DUE_AHEAD ? -1 : (refresh || sign_nx != nx) ? 0 : first_due(0);
     for (int s = 0; s < nb; s++) {
-      const double this_t = t_Gyr + dtg * (double)(jt + s);
       // same order of RNG draws as the reference: update_floor_sign (dynamo.f90:196-198) may
       // draw Bfloor_sign, then the first pde of the step redraws the layer signs if flagged
       // or if the grid size changed (floor_field.f90:55-79)
+      const double this_t = t_Gyr + dtg * (double)(jt + s);
       const bool due = this_t - t_last > tmk;
-      if (due || refresh || sign_nx != nx) {
+      if (MAG_WARP_DUE_AHEAD ? s == s_evt : (due || refresh || sign_nx != nx)) {
 #ifdef MAG_PHASE_CLOCKS
         const long long _r0 = clock64();
 #endif
@@ -531,24 +570,39 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
         if (due) t_last = this_t;
         refresh = false; sign_nx = nx;
         load_signed_floor();
+        if (MAG_WARP_DUE_AHEAD) s_evt = first_due(s + 1);
 #ifdef MAG_PHASE_CLOCKS
         if (lane == 0) { atomicAdd(&g_phase_clk[8], (unsigned long long)(clock64() - _r0)); atomicAdd(&g_phase_clk[9], 1ull); }
 #endif
       }
       const bool last_step = jt + s == nsteps;
-      if (JM >= 0 || PPL <= MAG_WARP_UNROLL_MAXPPL) {  // three stages unrolled: their shuffles and chains overlap
+      if ((JM >= 0 && MAG_WARP_UNROLL_JM) || PPL <= MAG_WARP_UNROLL_MAXPPL) {  // three stages unrolled: their shuffles and chains overlap
         warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg0, dz0, mBs, mBu, mAs, mAu);
         warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg1, dz1, mBs, mBu, mAs, mAu);
         if (last_step) save_alp();
         warp_stage<PPL, MODE, JM, true>(S, wsa, tab, lane, tm, jm, dg2, 0.0, mBs, mBu, mAs, mAu);
       } else {         // one stage body, looped: a three times smaller instruction footprint
+        // save_alp() runs before the third stage of the snapshot's last step: the stage loop stops there once, instead of
+        // testing for it (a taken branch around the call) in every stage
+        int st = 0, stop = (MAG_WARP_STAGE_LOOP2 && last_step) ? 2 : 3;
+        for (;;) {
 #pragma unroll 1
-        for (int st = 0; st < 3; st++) {
-          const double dg = rs->stage_dg[st], dz = rs->stage_dz[st];
-          if (st == 2 && last_step) save_alp();
-          warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg, dz, mBs, mBu, mAs, mAu);
-          if (PPL > WARP_LATE_GHOSTS_MAXPPL) warp_ghosts<PPL, MODE, JM>(S, lane, tm, jm);
+          for (; st < stop; st++) {
+            double dg, dz;
+            if (MAG_WARP_OPAQUE_ADDR) { dg = lds_f64x(sdg + 8u * (unsigned)st); dz = lds_f64x(sdg + 24u + 8u * (unsigned)st); }   // stage_dz follows stage_dg
+            else { dg = rs->stage_dg[st]; dz = rs->stage_dz[st]; }
+            if (!MAG_WARP_STAGE_LOOP2 && st == 2 && last_step) save_alp();
+            warp_stage<PPL, MODE, JM, false>(S, wsa, tab, lane, tm, jm, dg, dz, mBs, mBu, mAs, mAu);
+            if (PPL > WARP_LATE_GHOSTS_MAXPPL) warp_ghosts<PPL, MODE, JM>(S, lane, tm, jm);
+            // the time update of the step (below), two terms per stage, inside the stage so that its serial chain of five
+            // additions hides behind the stage's arithmetic; the third stage adds stage_dz[2] = +0.0 to a positive t: exact.
+            if (PPL <= WARP_T_IN_STAGE_MAXPPL) { t = t + dg; t = t + dz; }
+          }
+          if (st == 3) break;
+          save_alp();
+          stop = 3;
         }
+        if (PPL <= WARP_T_IN_STAGE_MAXPPL) continue;
       }
       // t = t + dt*gam1 ; ttmp = t + dt*zet1 ; t = ttmp + dt*gam2 ; ttmp = t + dt*zet2 ; t = ttmp + dt*gam3
       double tt = t + dg0;
@@ -625,12 +679,29 @@ __device__ __noinline__ bool warp_loop(Gal& G, RkShared* rs) {
 
 // Registers per lane for a grid of nx points: the two outer alp_m ghost entries must still
 // fall into a lane (slots up to P+4 < 32*PPL); 0 if the warp path does not take this grid.
+#ifndef MAG_WARP_CAND_SET
+#define MAG_WARP_CAND_SET 0
+#endif
+#if MAG_WARP_CAND_SET == 0
+#define MAG_WARP_CANDS {4, 5, 6, 8, 11}
+#elif MAG_WARP_CAND_SET == 1
+#define MAG_WARP_CANDS {4, 6, 8, 11}
+#elif MAG_WARP_CAND_SET == 2
+#define MAG_WARP_CANDS {4, 5, 8, 11}
+#elif MAG_WARP_CAND_SET == 3
+#define MAG_WARP_CANDS {4, 8, 11}
+#else
+#define MAG_WARP_CANDS {4, 6, 11}
+#endif
 __device__ __forceinline__ int warp_ppl(int nx) {
   const int P = nx - 2 * MAG_NGHOST - 1;
-  const int cand[5] = {4, 5, 6, 8, 11};
-  const int ncand = 5;
-  for (int c = 0; c < ncand; c++)
+  const int cand[] = MAG_WARP_CANDS;
+  const int ncand = (int)(sizeof(cand) / sizeof(cand[0]));
+  for (int c = 0; c < ncand; c++) {
+    // MAG_WARP_ALIGNED4 = 2: the four-register loop only takes grids that fill their last lane (one body, no alignment switch)
+    if (MAG_WARP_ALIGNED4 == 2 && cand[c] == 4 && (P + WARP_J0) % 4 != 3) continue;
     if (P + WARP_J0 + 3 < 32 * cand[c]) return cand[c];
+  }
   return 0;
 }
 // (R_kappa = 1, the reference's default, is folded into the alp_m stencil chain; other values
@@ -644,8 +715,10 @@ __device__ __forceinline__ bool warp_dispatch(Gal& G, RkShared* rs) {
   // the default grid (p_nx_ref = 101: nx = 107, most of the work) has its own instantiation with
   // a compile-time outer alignment and the three stages unrolled
   if (MAG_WARP_SPECIALIZE_DEFAULT && G.nx == 107) return warp_loop<4, MAG_W4_MODE, 3>(G, rs);
+  // the outer Dirichlet point in the last register of its lane (the default grid among others): no alignment switch in the stage
+  if (MAG_WARP_ALIGNED4 && warp_ppl(G.nx) == 4 && (G.nx - 2 * MAG_NGHOST - 1 + WARP_J0) % 4 == 3) return warp_loop<4, MAG_W4_MODE, 3>(G, rs);
   switch (warp_ppl(G.nx)) {
-    case 4: return warp_loop<4, MAG_W4_MODE, -1>(G, rs);
+    case 4: if (MAG_WARP_ALIGNED4 == 2) return false; return warp_loop<4, MAG_W4_MODE, -1>(G, rs);
     case 5: return warp_loop<5, WM_WSM, -1>(G, rs);
     case 6: return warp_loop<6, WM_WSM2, -1>(G, rs);
     case 8: return warp_loop<8, WM_ALLG, -1>(G, rs);

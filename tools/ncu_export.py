@@ -1,6 +1,8 @@
 """Box-side: turns an .ncu-rep into two small CSV files (the report itself can exceed what gpurun brings back):
-<out>_raw.csv (every metric of every captured launch) and <out>_source.csv (the `top` hottest SASS lines by samples)."""
+<out>_raw.csv (every metric of every captured launch) and <out>_source.csv (the `top` hottest SASS lines by samples;
+top = 0: every line in address order, gzip-compressed, <out>_source_all.csv.gz)."""
 import csv
+import gzip
 import io
 import subprocess
 import sys
@@ -16,6 +18,16 @@ if hdr_i is not None:
     hdr = rows[hdr_i]
     data = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
     col = hdr.index("# Samples")
+    if top == 0:
+        keep = [i for i, h in enumerate(hdr) if h in ("Address", "Source", "# Samples", "Instructions Executed", "Thread Instructions Executed",
+                                                        "Warp Stall Sampling (All Samples)", "Warp Stall Sampling (Not-issued Samples)")
+                or (h.startswith("stall_") and "Not Issued" not in h)]
+        with gzip.open(out + "_source_all.csv.gz", "wt", newline="") as f:
+            w = csv.writer(f)
+            w.writerow([hdr[i] for i in keep])
+            for r in data:
+                w.writerow([r[i] for i in keep])
+        top = 400
     data.sort(key=lambda r: -int(r[col] or 0))
     with open(out + "_source.csv", "w", newline="") as f:
         w = csv.writer(f)

@@ -15,10 +15,11 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     nsteps_max = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # > 0: cap the steps per snapshot, so that no single history sets the kernel time
+    first = int(sys.argv[4]) if len(sys.argv) > 4 else 196      # first synthetic galaxy id (40000 + 25000 galaxies + k = 40: the probe's chunk)
     d = np.load(os.path.join(ROOT, "tests", "golden", "example_input.npz"))
     t, base = d["t_gyr"], d["inputs"]
-    inputs = synthetic_histories(base, n, first=196)
-    ids = galaxy_ids(n, first=196)
+    inputs = synthetic_histories(base, n, first=first)
+    ids = galaxy_ids(n, first=first)
     for g in range(n):
         valid = np.nonzero(inputs[0, g] >= 0.5)[0]
         if valid.size > k:

@@ -133,11 +133,12 @@ def main():
         ids = galaxy_ids(n, first=30000)
         s.set_heavy_policy(mode=0)
         want = s.run(ids, t, syn)
-        n2 = 12500
-        syn2 = synthetic_histories(base, n2, first=20000)
-        ids2 = galaxy_ids(n2, first=20000)
+        n2 = int(os.environ.get("MAG_PROBE_VARIANT_N", "12500"))          # 25000 + first 40000: the probe's "mid" chunk (throughput, no tail)
+        first2 = int(os.environ.get("MAG_PROBE_VARIANT_FIRST", "20000"))
+        syn2 = synthetic_histories(base, n2, first=first2)
+        ids2 = galaxy_ids(n2, first=first2)
         r, tm, wall = timed(s, ids2, t, syn2)
-        report("default build, light only, 12500", s, r, tm, wall, n2)
+        report(f"default build, light only, {n2}", s, r, tm, wall, n2)
         s.close()
         for lib in os.environ["MAG_PROBE_LIBS"].split(","):
             S._LIB = None
@@ -151,7 +152,7 @@ def main():
             print(f"{os.path.basename(lib)}: results {'bit-identical to' if same else 'DIFFER from'} the default build "
                   f"(max abs profile difference {np.abs(want['profiles'] - got['profiles']).max():.2e})", flush=True)
             r, tm, wall = timed(v, ids2, t, syn2)
-            report(f"{os.path.basename(lib)} light only, 12500", v, r, tm, wall, n2)
+            report(f"{os.path.basename(lib)} light only, {n2}", v, r, tm, wall, n2)
             v.close()
         return
     s.close()
