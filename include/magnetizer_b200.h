@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MAG_ABI_VERSION 2
+#define MAG_ABI_VERSION 3
 
 /* Number of per-galaxy input time series, in the order read by
  * load_input_parameters (source/input_parameters.f90:158-170). */
@@ -138,7 +138,7 @@ typedef struct mag_params {
   int32_t p_simplified_pressure;  /* 1 */
   int32_t p_halo_contraction;     /* 1 */
   int32_t p_enable_P2;            /* 0 */
-  int32_t Dyn_quench;             /* 1 */
+  int32_t Dyn_quench;             /* 1; 0 (nvar = 2, no alp_m equation, no 'alp_m' rows: var module, gutsdynamo.f90:28-43) runs on the generic path */
   int32_t Alg_quench;             /* 0; 1 is implemented on the generic (any-nx) path: alp = alp_k/(1+B^2/Beq^2), gutsdynamo.f90:202-203 */
   int32_t Damp;                   /* 0 */
   int32_t lFloor;                 /* 1 */
@@ -146,12 +146,17 @@ typedef struct mag_params {
   int32_t p_time_varying_floor;   /* 1 */
   int32_t p_limit_turbulent_scale;/* 1 */
   int32_t p_allow_positive_shears;/* 0 */
-  int32_t seed_choice;            /* 0 = 'random' (only one implemented) */
+  int32_t seed_choice;            /* p_seed_choice, seed_field.f90:37-62: MAG_SEED_RANDOM (0, default), MAG_SEED_FRACTION, MAG_SEED_DECAYING;
+                                     'floor' is not implemented */
   /* outflow_parameters (:303-330), source/outflow.f90:24-121 -- all five prescriptions are
    * implemented: Uz enters the hoisted coefficients of the RHS (vertical advection of Br, Bp,
    * alp_m; floor-field source; critical dynamo number) and the 'Uz' output row */
   int32_t outflow_type;           /* MAG_OUTFLOW_*: 0 = 'no_outflow' */
-  int32_t reserved[6];
+  int32_t p_neumann_boundary_condition_rmax; /* 0; 1: dBr/dr = dBp/dr = 0 at r = R (impose_bc, gutsdynamo.f90:63-74), generic path */
+  int32_t p_use_fixed_physical_grid;         /* 0; 1: r_max = p_rmax_over_rdisk x the largest r_disk of the history, adjust_grid does
+                                                nothing (grid.f90:69-73, :159-162) */
+  int32_t p_nn_seed;                         /* 2 ('decaying' seed) */
+  int32_t reserved[3];
   double p_outflow_Lsn;           /* 1d38 */
   double p_outflow_fOB;           /* 0.7f */
   double p_outflow_etaSN;         /* 9.4d-3 */
@@ -161,7 +166,13 @@ typedef struct mag_params {
   double p_outflow_nu0;           /* 0.5 */
   double p_outflow_alphahot;      /* -3.2f */
   double p_outflow_Vhot;          /* 425 */
+  double p_r_seed_decay;          /* 15 kpc ('decaying' seed, global_input_parameters.f90:151) */
 } mag_params_t;
+
+/* p_seed_choice (source/seed_field.f90:37-62) */
+#define MAG_SEED_RANDOM 0
+#define MAG_SEED_FRACTION 1
+#define MAG_SEED_DECAYING 2
 
 /* p_outflow_type (source/global_input_parameters.f90:306, source/outflow.f90:63-95) */
 #define MAG_OUTFLOW_NONE 0

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-MAG_ABI_VERSION = 2
+MAG_ABI_VERSION = 3
 MAG_NINPUT = 13
 MAG_INVALID = -99999.0
 
@@ -31,6 +31,8 @@ MAG_RNG_XORSHIFT1024S = 1
 
 # p_outflow_type (outflow.f90:63-95)
 OUTFLOW_TYPES = ("no_outflow", "vturb", "wind", "superbubble_simple", "superbubble")
+# p_seed_choice (seed_field.f90:37-62); 'floor' is not implemented
+SEED_CHOICES = ("random", "fraction", "decaying")
 
 MAG_FLAG_UNINIT_R0 = 1
 MAG_FLAG_SECANT = 2
@@ -90,7 +92,10 @@ class MagParams(C.Structure):
         ("p_allow_positive_shears", C.c_int32),
         ("seed_choice", C.c_int32),
         ("outflow_type", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("p_neumann_boundary_condition_rmax", C.c_int32),
+        ("p_use_fixed_physical_grid", C.c_int32),
+        ("p_nn_seed", C.c_int32),
+        ("reserved", C.c_int32 * 3),
         ("p_outflow_Lsn", C.c_double),
         ("p_outflow_fOB", C.c_double),
         ("p_outflow_etaSN", C.c_double),
@@ -100,6 +105,7 @@ class MagParams(C.Structure):
         ("p_outflow_nu0", C.c_double),
         ("p_outflow_alphahot", C.c_double),
         ("p_outflow_Vhot", C.c_double),
+        ("p_r_seed_decay", C.c_double),
     ]
 
     def as_dict(self):

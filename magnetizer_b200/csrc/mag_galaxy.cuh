@@ -115,6 +115,7 @@ struct Gal {
   // grid
   int nx;
   double dx, lambda, dr_kpc, r_max_kpc;
+  double r_max_kpc_history;   // p_rmax_over_rdisk x the largest r_disk of the input rows (input_parameters.f90:173)
   // profiles
   double delta_r_floor, v_code, tau_min, minh, maxetat;
   // floor
@@ -146,6 +147,9 @@ __device__ inline void load_input_parameters(Gal& G) {
   const int nz = G.a->nz;
   G.init_it = -1;
   G.max_it = nz;
+  double mx = input_at(G, MAG_IN_R_DISK, 1);
+  for (int i = 2; i <= nz; i++) mx = fmax(mx, input_at(G, MAG_IN_R_DISK, i));
+  G.r_max_kpc_history = mx * G.a->P.p_rmax_over_rdisk;
   for (int i = 1; i <= nz; i++) {
     const double rd = input_at(G, MAG_IN_R_DISK, i);
     if (rd >= G.a->P.p_rdisk_min && G.init_it < 0) G.init_it = i;
@@ -182,7 +186,8 @@ __device__ inline void construct_grid(Gal& G) {
   const int nxphys = G.a->P.p_nx_ref;
   G.nx = nxphys + 2 * MAG_NGHOST;
   G.dx = (1.0 - MAG_R_IN) / (double)(nxphys - 1);
-  G.r_max_kpc = __dmul_rn(G.a->P.p_rmax_over_rdisk, G.r_disk);
+  // p_use_fixed_physical_grid (grid.f90:69-73): the largest disc of the history sets the grid once and for all
+  G.r_max_kpc = G.a->P.p_use_fixed_physical_grid ? G.r_max_kpc_history : __dmul_rn(G.a->P.p_rmax_over_rdisk, G.r_disk);
   double* x = G.A(A_X);
   double* rk = G.A(A_RKPC);
   for (int i = G.lane; i < G.nx; i += 32) {
@@ -214,15 +219,20 @@ __device__ __forceinline__ double rescale_at(const double* y, int n, int i, int 
 // impose_bc (gutsdynamo.f90:55-86): Dirichlet for Br,Bp at both ends, Neumann for alp_m
 __device__ inline void impose_bc(const Gal& G, double* f0, double* f1, double* f2) {
   const int nx = G.nx, l = G.lane;
+  // p_neumann_boundary_condition_rmax (:63-74): Br, Bp symmetric about r = R and the outer point left alone;
+  // without Dyn_quench there is no alp_m column (nvar = 2, :77-82): f2 stays at its initial zero
+  const bool neumann = G.a->P.p_neumann_boundary_condition_rmax != 0, dyn = G.a->P.Dyn_quench != 0;
   if (l < MAG_NGHOST) {
     const int ix = l + 1;                                   // 1-based ghost index
     const int a = ix - 1, ma = 2 * (MAG_NGHOST + 1) - ix - 1;
     const int b = nx - ix, mb = nx + 1 - 2 * (MAG_NGHOST + 1) + ix - 1;
-    f0[a] = -f0[ma]; f1[a] = -f1[ma]; f2[a] = f2[ma];
-    f0[b] = -f0[mb]; f1[b] = -f1[mb]; f2[b] = f2[mb];
+    f0[a] = -f0[ma]; f1[a] = -f1[ma];
+    if (neumann) { f0[b] = f0[mb]; f1[b] = f1[mb]; }
+    else { f0[b] = -f0[mb]; f1[b] = -f1[mb]; }
+    if (dyn) { f2[a] = f2[ma]; f2[b] = f2[mb]; }
   } else if (l == MAG_NGHOST) {
     f0[MAG_NGHOST] = 0.0; f1[MAG_NGHOST] = 0.0;
-    f0[nx - MAG_NGHOST - 1] = 0.0; f1[nx - MAG_NGHOST - 1] = 0.0;
+    if (!neumann) { f0[nx - MAG_NGHOST - 1] = 0.0; f1[nx - MAG_NGHOST - 1] = 0.0; }
   }
   __syncwarp();
 }
@@ -745,6 +755,8 @@ __device__ inline bool adjust_grid_geometry(Gal& G, int* nx_mid, bool* scaled, b
   double *x = G.A(A_X), *rk = G.A(A_RKPC);
   double* tmp = G.A(A_T0);
   *scaled = false; *extended = false;
+  *nx_mid = G.nx;
+  if (P.p_use_fixed_physical_grid) return true;   // grid.f90:159-162: do nothing
   if (G.nx != nx_def) {  // scale back to the default resolution
     const int nx_old = G.nx;
     for (int i = lane; i < nx_old; i += 32) tmp[i] = rk[i];
@@ -858,14 +870,35 @@ __device__ inline void refresh_signs(Gal& G) {
   __syncwarp();
 }
 
-// init_seed_field (seed_field.f90:27-63, 'random'): sequential draws on lane 0
+// x**n with integer n as gfortran compiles it (libgcc __powidf2: square and multiply from the low bit)
+__device__ __forceinline__ double pow_int(double x, int m) {
+  unsigned int n = m < 0 ? (unsigned int)(-m) : (unsigned int)m;
+  double y = (n % 2) ? x : 1.0;
+  while (n >>= 1) {
+    x = x * x;
+    if (n % 2) y *= x;
+  }
+  return m < 0 ? 1.0 / y : y;
+}
+// init_seed_field (seed_field.f90:27-63): 'random' (sequential draws on lane 0), 'fraction', 'decaying'
 __device__ inline void init_seed_field(Gal& G) {
   const int nx = G.nx;
   double *f0 = G.A(A_F0), *f1 = G.A(A_F1), *f2 = G.A(A_F2);
   const double* Beq = G.A(A_BEQ);
+  const double fs = G.a->P.frac_seed;
   for (int i = G.lane; i < nx; i += 32) f2[i] = 0.0;
-  if (G.lane == 0) {
-    const double fs = G.a->P.frac_seed;
+  if (G.a->P.seed_choice == MAG_SEED_FRACTION) {            // :38-41
+    for (int i = G.lane; i < nx; i += 32) { const double Bseed = fs * Beq[i]; f0[i] = -Bseed; f1[i] = Bseed; }
+  } else if (G.a->P.seed_choice == MAG_SEED_DECAYING) {     // :42-46
+    const double* x = G.A(A_X);
+    const double r1 = G.a->P.p_r_seed_decay / G.r_max_kpc;
+    const int nn = G.a->P.p_nn_seed;
+    for (int i = G.lane; i < nx; i += 32) {
+      const double Bseed = fs * Beq[i], r = x[i];
+      f0[i] = -Bseed * r * pow_int(1.0 - r, nn) * detmath::det_exp(-r / r1);
+      f1[i] = Bseed * r * pow_int(1.0 - r, nn) * detmath::det_exp(-r / r1);
+    }
+  } else if (G.lane == 0) {
     for (int i = 0; i < nx; i++) f0[i] = (fs * Beq[i]) * rng_normal_lane0(G.rng);
     for (int i = 0; i < nx; i++) f1[i] = (fs * Beq[i]) * rng_normal_lane0(G.rng);
   }
@@ -903,7 +936,7 @@ __device__ inline void pde_generic(Gal& G) {
   const double *Gc = G.A(A_G), *alp_k = G.A(A_ALPK), *sg = G.A(A_SIGN);
   double *p0 = G.A(A_P0), *p1 = G.A(A_P1), *p2 = G.A(A_P2), *alp = G.A(A_ALP);
   const double Rk = G.a->P.R_kappa;
-  const bool alg = G.a->P.Alg_quench != 0;
+  const bool alg = G.a->P.Alg_quench != 0, dyn = G.a->P.Dyn_quench != 0;
   const double *bz = G.A(A_BZ), *beq = G.A(A_BEQ);
   for (int i = G.lane; i < nx; i += 32) {
     const double Br = f0[i], Bp = f1[i], am = f2[i];
@@ -915,12 +948,13 @@ __device__ inline void pde_generic(Gal& G) {
     const double ir = cIR[i], c1 = cC1[i], cr = cCR[i];
     // total alpha: dynamical quenching, or -- Alg_quench -- alp_k/(1 + Bsqtot/Beq^2) with Bsqtot = Br^2+Bp^2+Bzmod^2
     // (gutsdynamo.f90:199-209; Bzmod is the estimate of the start of the step, dynamo.f90:179)
-    const double a = alg ? alp_k[i] / (1.0 + (Br * Br + Bp * Bp + bz[i] * bz[i]) / (beq[i] * beq[i])) : alp_k[i] + am;
+    const double a = alg ? alp_k[i] / (1.0 + (Br * Br + Bp * Bp + bz[i] * bz[i]) / (beq[i] * beq[i])) : (dyn ? alp_k[i] + am : alp_k[i]);
     alp[i] = a;
     p0[i] = -c1 * Br - cCA[i] * a * Bp + cr * (d2Br + ir * (dBr - Br * ir));
     p1[i] = Gc[i] * Br - c1 * Bp + cr * (d2Bp + ir * (dBp - Bp * ir)) + sg[i] * cFB[i] * (1.0 + cKDC[i] * a);
     p2[i] = cP3[i] * (a * (Br * Br + Bp * Bp) + cQC[i] * sqrt(fabs(a)) * Br * Bp) + cW[i] * am +
             Rk * cr * (d2am + dam * ir);
+    if (!dyn) p2[i] = 0.0;   // nvar = 2 (var module, gutsdynamo.f90:28-43): no alp_m equation, the third array stays zero
   }
   G.point_stages += nx;
   __syncwarp();
@@ -931,7 +965,8 @@ __device__ inline bool f_blew_up(const Gal& G) {
   const int nx = G.nx;
   const double *f0 = G.A(A_F0), *f1 = G.A(A_F1), *f2 = G.A(A_F2);
   bool bad = false;
-  for (int i = G.lane; i < nx; i += 32) bad = bad || (f0[i] > 1e8) || (f1[i] > 1e8) || (f2[i] > 1000.0);
+  const bool dyn = G.a->P.Dyn_quench != 0;   // :460: the alp_m test only with Dyn_quench
+  for (int i = G.lane; i < nx; i += 32) bad = bad || (f0[i] > 1e8) || (f1[i] > 1e8) || (dyn && f2[i] > 1000.0);
   return __any_sync(FULL, bad);
 }
 
@@ -1028,6 +1063,10 @@ __device__ inline void write_field_rows(Gal& G, int it) {
     if (q == MAG_Q_ALP && !alp_ok) q = MAG_Q_H;  // ts_arrays.f90:200-201: stale tmp (= h)
     const double* src = profile_source(G, q);
     double* dst = a->prof[qq] + (g * nz + (it - 1)) * nr;
+    if (q == MAG_Q_ALP_M && !a->P.Dyn_quench) {   // ts_arrays.f90:132-138: no 'alp_m' row without Dyn_quench
+      for (int i = lane; i < nr; i += 32) dst[i] = MAG_INVALID;
+      continue;
+    }
     for (int i = lane; i < nr; i += 32) dst[i] = rescale_at(src + ng, ni, i, nr);
   }
   if (a->n_scalar_q > 0 && a->scal[0]) {

@@ -312,7 +312,8 @@ void mag_params_default(mag_params_t* p) {
   p->p_variable_timesteps = 1; p->p_simplified_pressure = 1; p->p_halo_contraction = 1; p->p_enable_P2 = 0;
   p->Dyn_quench = 1; p->Alg_quench = 0; p->Damp = 0; p->lFloor = 1;
   p->p_space_varying_floor = 1; p->p_time_varying_floor = 1; p->p_limit_turbulent_scale = 1;
-  p->p_allow_positive_shears = 0; p->seed_choice = 0; p->outflow_type = MAG_OUTFLOW_NONE;
+  p->p_allow_positive_shears = 0; p->seed_choice = MAG_SEED_RANDOM; p->outflow_type = MAG_OUTFLOW_NONE;
+  p->p_neumann_boundary_condition_rmax = 0; p->p_use_fixed_physical_grid = 0; p->p_nn_seed = 2; p->p_r_seed_decay = 15.0;
   // outflow_parameters (global_input_parameters.f90:303-325)
   p->p_outflow_Lsn = 1e38; p->p_outflow_fOB = (double)0.7f; p->p_outflow_etaSN = 9.4e-3; p->p_tOB = 3.0; p->p_N_SN1OB = 40.0;
   p->p_outflow_hot_gas_density = 1.7e-27; p->p_outflow_nu0 = 0.5; p->p_outflow_alphahot = (double)-3.2f; p->p_outflow_Vhot = 425.0;
@@ -320,9 +321,11 @@ void mag_params_default(mag_params_t* p) {
 
 static bool params_supported(const mag_params_t& p) {
   return p.abi_version == MAG_ABI_VERSION && p.p_variable_timesteps == 1 && p.p_simplified_pressure == 1 &&
-         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && (p.Alg_quench == 0 || p.Alg_quench == 1) && p.Damp == 0 &&
+         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && (p.Dyn_quench == 0 || p.Dyn_quench == 1) && (p.Alg_quench == 0 || p.Alg_quench == 1) && p.Damp == 0 &&
          p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
-         p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice == 0 &&
+         p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice >= MAG_SEED_RANDOM && p.seed_choice <= MAG_SEED_DECAYING &&
+         (p.p_neumann_boundary_condition_rmax == 0 || p.p_neumann_boundary_condition_rmax == 1) &&
+         (p.p_use_fixed_physical_grid == 0 || p.p_use_fixed_physical_grid == 1) &&
          p.outflow_type >= MAG_OUTFLOW_NONE && p.outflow_type <= MAG_OUTFLOW_SUPERBUBBLE && p.p_nx_ref >= 8 &&
          (p.rng_kind == 0 || p.rng_kind == 1) && p.p_nx_MAX >= p.p_nx_ref + 6;
 }
@@ -493,7 +496,9 @@ static int launch_solve(mag_ctx* c, KernelArgs& a, int32_t g0, int32_t n, cudaSt
   a.cost_total = c->d_arena_top + 1;
   // the register loops hard-wire alp = alp_k + alp_m; algebraic quenching (gutsdynamo.f90:202-203) needs Bzmod in the
   // RHS at every step and runs on the any-nx generic path
-  a.use_fast = c->P.Alg_quench ? 0 : c->use_fast;
+  // ... and so do the Neumann outer boundary (the register loops fold the Dirichlet one into their stencil weights) and the
+  // runs without the alp_m equation
+  a.use_fast = (c->P.Alg_quench || c->P.p_neumann_boundary_condition_rmax || !c->P.Dyn_quench) ? 0 : c->use_fast;
   a.recs = c->d_recs; a.heads = c->d_heads; a.arena = c->d_arena; a.arena_top = c->d_arena_top; a.arena_cap = c->arena_cap;
   a.jobs = c->d_jobs; a.job_count = c->d_job_count; a.jobidx = c->d_jobidx;
   a.pdl_join = c->launch_pdl;

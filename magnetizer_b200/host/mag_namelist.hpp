@@ -146,11 +146,10 @@ struct OtherKey { const char* name; const char* dflt; int kind; };   // kind 0: 
 static const OtherKey kOtherKeys[] = {
     // dynamo_parameters
     {"alp_ceiling", ".true.", 0}, {"alp_squared", ".false.", 0}, {"krause", ".true.", 0}, {"advect", ".true.", 0},
-    {"turb_dif", ".true.", 0}, {"p_neumann_boundary_condition_rmax", ".false.", 0},
-    {"p_r_seed_decay", "15.0", 1}, {"p_nn_seed", "2", 1},   // only read by the seed choices that are rejected anyway
+    {"turb_dif", ".true.", 0},
     // grid_parameters
     {"p_rescale_field_for_shrinking_disks", ".true.", 0}, {"p_rescale_field_for_expanding_disks", ".false.", 0},
-    {"p_scale_back_f_array", ".true.", 0}, {"p_use_fixed_physical_grid", ".false.", 0}, {"p_interp_method", "simple", 0},
+    {"p_scale_back_f_array", ".true.", 0}, {"p_interp_method", "simple", 0},
     // ISM_and_disk_parameters
     {"p_check_hydro_solution", ".false.", 1}, {"p_use_fixed_turbulent_to_scaleheight_ratio", ".false.", 0},
     {"p_turbulent_to_scaleheight_ratio", "0.25", 1}, {"p_truncates_within_rreg", ".false.", 0},
@@ -191,11 +190,18 @@ inline RunConfig load_run_config(const std::string& path) {
   MAG_NL(p_variable_timesteps); MAG_NL(p_simplified_pressure); MAG_NL(p_halo_contraction); MAG_NL(p_enable_P2);
   MAG_NL(Dyn_quench); MAG_NL(Alg_quench); MAG_NL(Damp); MAG_NL(lFloor); MAG_NL(p_space_varying_floor);
   MAG_NL(p_time_varying_floor); MAG_NL(p_limit_turbulent_scale); MAG_NL(p_allow_positive_shears);
+  MAG_NL(p_neumann_boundary_condition_rmax); MAG_NL(p_use_fixed_physical_grid); MAG_NL(p_nn_seed); MAG_NL(p_r_seed_decay);
   MAG_NL(p_outflow_Lsn); MAG_NL(p_outflow_fOB); MAG_NL(p_outflow_etaSN); MAG_NL(p_tOB); MAG_NL(p_N_SN1OB);
   MAG_NL(p_outflow_hot_gas_density); MAG_NL(p_outflow_nu0); MAG_NL(p_outflow_alphahot); MAG_NL(p_outflow_Vhot);
 #undef MAG_NL
   std::string s;
-  if (nl.get("p_seed_choice", &s)) p.seed_choice = (Namelist::lower(s) == "random") ? 0 : 1;
+  if (nl.get("p_seed_choice", &s)) {
+    static const char* seeds[] = {"random", "fraction", "decaying"};
+    p.seed_choice = -1;
+    for (int k = 0; k < 3; k++) if (Namelist::lower(s) == seeds[k]) p.seed_choice = k;
+    if (p.seed_choice < 0)   // 'floor', or a name init_seed_field stops on (seed_field.f90:58-60)
+      throw std::runtime_error("parameter file sets p_seed_choice = " + s + ": this seed prescription is not implemented by the CUDA path");
+  }
   if (nl.get("p_outflow_type", &s)) {
     static const char* names[] = {"no_outflow", "vturb", "wind", "superbubble_simple", "superbubble"};
     p.outflow_type = -1;   // unknown prescription: mag_create rejects it (outflow.f90:92-94 stops)

@@ -112,9 +112,12 @@ void write_parameter_attributes(maghost::Hdf5Writer& w, const maghost::RunConfig
       {"p_IO_number_of_galaxies_in_chunks", fint(cfg.p_IO_number_of_galaxies_in_chunks)}, {"p_IO_compression", fbool(cfg.p_IO_compression)},
       {"p_IO_compression_level", fint(cfg.p_IO_compression_level)}, {"p_ncheckpoint", fint(cfg.p_ncheckpoint)}}));
   w.add_root_attribute("grid_parameters", nml_text("GRID_PARAMETERS", {{"p_nx_ref", fint(p.p_nx_ref)}, {"p_nx_MAX", fint(p.p_nx_MAX)},
-      {"p_rmax_over_rdisk", fnum(p.p_rmax_over_rdisk)}}));
+      {"p_rmax_over_rdisk", fnum(p.p_rmax_over_rdisk)}, {"p_use_fixed_physical_grid", fbool(p.p_use_fixed_physical_grid)}}));
   w.add_root_attribute("dynamo_parameters", nml_text("DYNAMO_PARAMETERS", {{"Dyn_quench", fbool(p.Dyn_quench)}, {"Alg_quench", fbool(p.Alg_quench)},
-      {"lFloor", fbool(p.lFloor)}, {"Damp", fbool(p.Damp)}, {"frac_seed", fnum(p.frac_seed)}, {"p_seed_choice", "\"random\""},
+      {"lFloor", fbool(p.lFloor)}, {"Damp", fbool(p.Damp)}, {"frac_seed", fnum(p.frac_seed)},
+      {"p_seed_choice", std::string("\"") + (p.seed_choice == MAG_SEED_FRACTION ? "fraction" : p.seed_choice == MAG_SEED_DECAYING ? "decaying" : "random") + "\""},
+      {"p_r_seed_decay", fnum(p.p_r_seed_decay)}, {"p_nn_seed", fint(p.p_nn_seed)},
+      {"p_neumann_boundary_condition_rmax", fbool(p.p_neumann_boundary_condition_rmax)},
       {"C_alp", fnum(p.C_alp)}, {"C_floor", fnum(p.C_floor)}, {"p_floor_kappa", fnum(p.p_floor_kappa)},
       {"p_space_varying_floor", fbool(p.p_space_varying_floor)}, {"p_time_varying_floor", fbool(p.p_time_varying_floor)},
       {"fmag", fnum(p.fmag)}, {"R_kappa", fnum(p.R_kappa)}}));

@@ -123,7 +123,11 @@ static void params_default(mag_params_t* p) {
   p->p_time_varying_floor = 1;                          // :188
   p->p_limit_turbulent_scale = 1;                       // :221
   p->p_allow_positive_shears = 0;                       // :243
-  p->seed_choice = 0;                                   // :150 'random'
+  p->seed_choice = MAG_SEED_RANDOM;                     // :150 'random'
+  p->p_neumann_boundary_condition_rmax = 0;             // :170
+  p->p_use_fixed_physical_grid = 0;                     // :112
+  p->p_nn_seed = 2;                                     // :152
+  p->p_r_seed_decay = 15.0;                             // :151
   p->outflow_type = MAG_OUTFLOW_NONE;                   // :306 'no_outflow'
   // outflow_parameters, :303-325 (literals without d0 are single precision)
   p->p_outflow_Lsn = 1e38;                              // :308
@@ -139,9 +143,9 @@ static void params_default(mag_params_t* p) {
 
 static bool params_supported(const mag_params_t& p) {
   return p.abi_version == MAG_ABI_VERSION && p.p_variable_timesteps == 1 && p.p_simplified_pressure == 1 &&
-         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && p.Dyn_quench == 1 && (p.Alg_quench == 0 || p.Alg_quench == 1) &&
+         p.p_halo_contraction == 1 && p.p_enable_P2 == 0 && (p.Dyn_quench == 0 || p.Dyn_quench == 1) && (p.Alg_quench == 0 || p.Alg_quench == 1) &&
          p.Damp == 0 && p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
-         p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice == 0 &&
+         p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice >= MAG_SEED_RANDOM && p.seed_choice <= MAG_SEED_DECAYING &&
          p.outflow_type >= MAG_OUTFLOW_NONE && p.outflow_type <= MAG_OUTFLOW_SUPERBUBBLE && p.p_nx_ref >= 8 &&
          (p.rng_kind == 0 || p.rng_kind == 1);
 }
@@ -370,7 +374,7 @@ struct Galaxy {
     x.assign(nx, 0.0);
     r_kpc.assign(nx, 0.0);
     for (int i = 1; i <= nx; i++) x[i - 1] = r_in - nxghost * dx + ((double)i - 1.0) * dx;
-    r_max_kpc = P.p_rmax_over_rdisk * r_disk;
+    r_max_kpc = P.p_use_fixed_physical_grid ? r_max_kpc_history : P.p_rmax_over_rdisk * r_disk;   // :69-73
     for (int i = 0; i < nx; i++) r_kpc[i] = x[i] * r_max_kpc;
     dr_kpc = dx * r_max_kpc;
     lambda = h0_kpc / r_max_kpc;
@@ -378,6 +382,7 @@ struct Galaxy {
 
   // adjust_grid, :143-297 (default switches)
   void adjust_grid() {
+    if (P.p_use_fixed_physical_grid) return;   // :159-162
     const double GRID_ADJ_THRES = (double)0.05f;
     const int nvar = 3;
     const int nx_def = P.p_nx_ref + 2 * nxghost;
@@ -886,9 +891,39 @@ struct Galaxy {
   }
 
   // -------------------------------------------------------------- seed_field.f90
-  // init_seed_field, :27-63 ('random')
+  // x**n with integer n as gfortran compiles it (libgcc __powidf2: square and multiply from the low bit)
+  static double pow_int(double xx, int mm) {
+    unsigned int n = mm < 0 ? (unsigned int)(-mm) : (unsigned int)mm;
+    double y = (n % 2) ? xx : 1.0;
+    while (n >>= 1) {
+      xx = xx * xx;
+      if (n % 2) y *= xx;
+    }
+    return mm < 0 ? 1.0 / y : y;
+  }
+  // init_seed_field, :27-63 ('random', 'fraction', 'decaying')
   void init_seed_field() {
     std::fill(f.begin(), f.end(), 0.0);
+    if (P.seed_choice == MAG_SEED_FRACTION) {          // :38-41
+      for (int i = 0; i < nx; i++) {
+        const double Bseed = P.frac_seed * Beq[i];
+        f[i] = -Bseed;
+        f[(size_t)nx + i] = Bseed;
+      }
+      return;
+    }
+    if (P.seed_choice == MAG_SEED_DECAYING) {          // :42-46
+      const double r1 = P.p_r_seed_decay / r_max_kpc;
+      for (int i = 0; i < nx; i++) {
+        const double Bseed = P.frac_seed * Beq[i];
+        const double r = x[i];
+        // (1-r)**p_nn_seed: integer power, gfortran multiplies (pow_int below)
+        const double shape = -Bseed * r * pow_int(1.0 - r, P.p_nn_seed) * m_exp(-r / r1);
+        f[i] = shape;
+        f[(size_t)nx + i] = Bseed * r * pow_int(1.0 - r, P.p_nn_seed) * m_exp(-r / r1);
+      }
+      return;
+    }
     for (int var = 0; var < 2; var++)
       for (int i = 0; i < nx; i++) {
         double Bseed = P.frac_seed * Beq[i];
@@ -900,15 +935,19 @@ struct Galaxy {
   // impose_bc, :55-86 (Dirichlet at both ends for Br,Bp; Neumann for alp_m)
   void impose_bc(double* ff) const {
     double* Br = ff; double* Bp = ff + nx; double* am = ff + 2 * (size_t)nx;
+    const bool neumann = P.p_neumann_boundary_condition_rmax != 0;
     Br[nxghost] = 0.0; Bp[nxghost] = 0.0;
-    Br[nx - nxghost - 1] = 0.0; Bp[nx - nxghost - 1] = 0.0;
+    if (!neumann) { Br[nx - nxghost - 1] = 0.0; Bp[nx - nxghost - 1] = 0.0; }
     for (int ix = 1; ix <= nxghost; ix++) {
       int a = ix - 1, ma = 2 * (nxghost + 1) - ix - 1;
       int b = nx + 1 - ix - 1, mb = nx + 1 - 2 * (nxghost + 1) + ix - 1;
       Br[a] = -Br[ma]; Bp[a] = -Bp[ma];
-      Br[b] = -Br[mb]; Bp[b] = -Bp[mb];
-      am[a] = am[ma];
-      am[b] = am[mb];
+      if (neumann) { Br[b] = Br[mb]; Bp[b] = Bp[mb]; }   // :70-72, symmetric about r = R
+      else { Br[b] = -Br[mb]; Bp[b] = -Bp[mb]; }
+      if (P.Dyn_quench) {                                // :77-82
+        am[a] = am[ma];
+        am[b] = am[mb];
+      }
     }
   }
   // estimate_Bzmod, :101-114
@@ -942,7 +981,7 @@ struct Galaxy {
       const double r = x[i], hh = h[i], et = etat[i], uz = Uz[i];
       // gutsdynamo.f90:199-209: Bsqtot = Br**2 + Bp**2 + Bzmod**2; Alg_quench takes precedence over Dyn_quench
       const double Bsqtot = Br[i] * Br[i] + Bp[i] * Bp[i] + Bzmod[i] * Bzmod[i];
-      const double a = P.Alg_quench ? alp_k[i] / (1.0 + Bsqtot / (Beq[i] * Beq[i])) : alp_k[i] + alp_m[i];
+      const double a = P.Alg_quench ? alp_k[i] / (1.0 + Bsqtot / (Beq[i] * Beq[i])) : (P.Dyn_quench ? alp_k[i] + alp_m[i] : alp_k[i]);
       alp[i] = a;
       const double detatdr = 1.0 / 3 * l[i] * 0.0 + 1.0 / 3 * v[i] * 0.0;  // dvdr = dldr = 0
       const double Dyn_gen = G[i] * a * (hh * hh * hh) / (et * et);
@@ -968,6 +1007,7 @@ struct Galaxy {
                    ctau * 3 * et / pi32 / hh * std::sqrt(std::fabs(Dyn_gen)) * Br[i] * Bp[i] / beq2 + Rm_inv * alp_m[i]) -
               C_a * alp_m[i] * uz / hh + R_kappa * et * C_d / (hh * hh) * alp_m[i] +
               R_kappa * et * lam2 * (w_d2am[i] + w_dam[i] / r) + R_kappa * detatdr * lam2 * w_dam[i];
+      if (!P.Dyn_quench) d3[i] = 0.0;   // nvar = 2 (var module, :28-43): no alp_m equation; the third array stays at its initial zero
     }
   }
 
@@ -978,7 +1018,7 @@ struct Galaxy {
     if (m > 1e8) *ok = false;
     double m3 = ff[2 * (size_t)nx];
     for (int i = 1; i < nx; i++) m3 = std::max(m3, ff[2 * (size_t)nx + i]);
-    if (m3 > 1000) *ok = false;
+    if (P.Dyn_quench && m3 > 1000) *ok = false;
   }
 
   vec w_pdef, w_ftmp;
@@ -1040,7 +1080,7 @@ struct Galaxy {
     ts_set(MAG_Q_BR, it, F(0) + nxghost, ni);
     ts_set(MAG_Q_BP, it, F(1) + nxghost, ni);
     ts_set(MAG_Q_BZMOD, it, Bzmod.data() + nxghost, ni);
-    ts_set(MAG_Q_ALP_M, it, F(2) + nxghost, ni);
+    if (P.Dyn_quench) ts_set(MAG_Q_ALP_M, it, F(2) + nxghost, ni);   // ts_arrays.f90:132-138
     ts_set(MAG_Q_H, it, h.data() + nxghost, ni);
     ts_set(MAG_Q_OMEGA, it, Om.data() + nxghost, ni);
     ts_set(MAG_Q_SHEAR, it, G.data() + nxghost, ni);

@@ -411,6 +411,57 @@ def test_algebraic_quenching(oracle, example_input):
         s.close()
 
 
+_SWITCH_REF = {}
+_SWITCH_CASES = [
+    # (id, settings, runs on the register loops?)
+    ("neumann_outer_bc", dict(p_neumann_boundary_condition_rmax=1), False),       # gutsdynamo.f90:63-74
+    ("fixed_physical_grid", dict(p_use_fixed_physical_grid=1), True),              # grid.f90:69-73, :159-162
+    ("seed_fraction", dict(seed_choice=1), True),                                  # seed_field.f90:38-41
+    ("seed_decaying", dict(seed_choice=2, p_r_seed_decay=8.0, p_nn_seed=3), True),  # seed_field.f90:42-46
+    ("alg_quench_without_dyn_quench", dict(Alg_quench=1, Dyn_quench=0), False),    # nvar = 2, gutsdynamo.f90:28-43, :199-209
+    ("kinematic_no_quenching", dict(Dyn_quench=0), False),
+]
+
+
+@pytest.mark.parametrize("name,settings,fast", _SWITCH_CASES, ids=[c[0] for c in _SWITCH_CASES])
+def test_more_physics_switches(oracle, example_input, name, settings, fast):
+    """the Neumann outer boundary, the fixed physical grid, the deterministic seed prescriptions and
+    the runs without the alp_m equation (nvar = 2: no 'alp_m' rows) -- 48 example + 16 synthetic galaxies each,
+    on one-warp and on four-warp teams."""
+    from magnetizer_b200.solver import DynamoSolver
+    from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
+    t, inputs = example_input
+    ex = np.arange(1, 49, dtype=np.int32)
+    syn = synthetic_histories(inputs, 16, first=9000)
+    ids = np.concatenate([ex, galaxy_ids(16, first=9000)])
+    allin = np.ascontiguousarray(np.concatenate([inputs[:, ex - 1, :], syn], axis=1))
+    prof, scal = ("Br", "Bp", "alp_m", "Bzmod", "h", "n", "alp", "rkpc"), ("Bmax", "Bmax_idx", "dt", "rmax")
+    p = oracle.default_params()
+    for k, v in settings.items():
+        setattr(p, k, v)
+    ora = oracle.solve_batch(p, ids, t, allin, profiles=prof, scalars=scal)
+    if "ref" not in _SWITCH_REF:
+        _SWITCH_REF["ref"] = oracle.solve_batch(oracle.default_params(), ids, t, allin, profiles=prof, scalars=scal)
+    assert not np.array_equal(ora["profiles"][0], _SWITCH_REF["ref"]["profiles"][0])   # the switch changes Br
+    am = ora["profiles"][prof.index("alp_m")]
+    assert (am > -9e4).any() == bool(p.Dyn_quench)                                 # ts_arrays.f90:132-138
+    if name == "fixed_physical_grid":                                              # one radial grid for the whole history
+        rk = ora["profiles"][prof.index("rkpc")]
+        for g in range(0, len(ids), 7):
+            rows = rk[g][rk[g][:, -1] > -9e4]
+            assert len(rows) == 0 or np.ptp(rows[:, -1]) == 0.0
+    s = DynamoSolver(params=p, device=0)
+    try:
+        for mode in (0, 2):
+            s.set_heavy_policy(mode=mode)
+            gpu = s.run(ids, t, allin, profiles=prof, scalars=scal)
+            rep = compare(gpu, ora, failed_runs="relaxed")
+            print(name, "heavy mode", mode, "worst:", max(rep.values()), "statuses:", sorted(set(ora["status"].tobytes().decode())),
+                  "replays", s.info()["fast_path_replays"])
+    finally:
+        s.close()
+
+
 def test_heavy_teams_every_grid_class(oracle, example_input):
     """k_evolve_heavy (four warps per galaxy, mag_rk_fast.cuh): all galaxies forced onto it.  The
     example histories reach nx = 107 .. 330, i.e. the 1-, 2- and 3-points-per-thread loops; results
