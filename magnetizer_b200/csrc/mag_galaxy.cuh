@@ -115,6 +115,7 @@ struct Gal {
   // grid
   int nx;
   double dx, lambda, dr_kpc, r_max_kpc;
+  double seed_r1;             // p_r_seed_decay / r_max_kpc of the grid the next seed field is drawn on (from the snapshot record)
   double r_max_kpc_history;   // p_rmax_over_rdisk x the largest r_disk of the input rows (input_parameters.f90:173)
   // profiles
   double delta_r_floor, v_code, tau_min, minh, maxetat;
@@ -891,7 +892,7 @@ __device__ inline void init_seed_field(Gal& G) {
     for (int i = G.lane; i < nx; i += 32) { const double Bseed = fs * Beq[i]; f0[i] = -Bseed; f1[i] = Bseed; }
   } else if (G.a->P.seed_choice == MAG_SEED_DECAYING) {     // :42-46
     const double* x = G.A(A_X);
-    const double r1 = G.a->P.p_r_seed_decay / G.r_max_kpc;
+    const double r1 = G.seed_r1;
     const int nn = G.a->P.p_nn_seed;
     for (int i = G.lane; i < nx; i += 32) {
       const double Bseed = fs * Beq[i], r = x[i];

@@ -42,8 +42,9 @@ struct SnapRec {       // dense [ngal][nz]
   uint32_t gflags;     // MAG_FLAG_* raised by the profile phase up to and including this snapshot
   int32_t pad;
   long long off;       // arena offset (doubles) of R_COUNT arrays, each `nx` long
-  long long off_pre;   // arena offset of Beq on the pre-adjust grid [nx_pre] (SR_RESEED only)
+  long long off_pre;   // arena offset of Beq and x on the pre-adjust grid, 2 x [nx_pre] (SR_RESEED only)
   double dt, t_Gyr, lambda, delta_r_floor, tau_min, v_code;
+  double seed_r1;      // p_r_seed_decay / r_max_kpc of the grid a seed field of this snapshot is drawn on ('decaying' seed)
 };
 struct GalHead {       // [chunk]
   int32_t init_it, max_it, error;
@@ -152,7 +153,7 @@ __device__ inline void run_chain_job(const KernelArgs& a, int j) {
 }
 
 // writes the record of snapshot `it` from the warp's workspace
-__device__ inline bool write_record(Gal& G, int it, int flags, int nx_pre, int nx_mid, long long off_pre) {
+__device__ inline bool write_record(Gal& G, int it, int flags, int nx_pre, int nx_mid, long long off_pre, double seed_r1 = 0.0) {
   const KernelArgs* a = G.a;
   const int nx = G.nx;
   const long long off = arena_alloc(a, G.lane, (long long)R_COUNT * nx);
@@ -167,7 +168,7 @@ __device__ inline bool write_record(Gal& G, int it, int flags, int nx_pre, int n
     R.flags = flags | SR_VALID; R.nx = nx; R.nx_pre = nx_pre; R.nx_mid = nx_mid; R.nsteps = G.nsteps;
     R.status = (int)G.status; R.off = off; R.off_pre = off_pre; R.gflags = G.flags; R.pad = 0;
     R.dt = G.dt; R.t_Gyr = G.t_Gyr; R.lambda = G.lambda; R.delta_r_floor = G.delta_r_floor;
-    R.tau_min = G.tau_min; R.v_code = G.v_code;
+    R.tau_min = G.tau_min; R.v_code = G.v_code; R.seed_r1 = seed_r1;
   }
   __syncwarp();
   return true;
@@ -218,6 +219,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
     const int nx_pre = G.nx;
     int nx_mid = G.nx;
     long long off_pre = -1;
+    const double seed_r1 = P.p_r_seed_decay / G.r_max_kpc;   // seeds are drawn before adjust_grid (dynamo.f90:113-131)
     if (G.r_disk < P.p_rdisk_min || G.Mgas_disk < P.Mgas_disk_min) {
       elliptical = true;
       fl |= SR_TRAP;
@@ -228,10 +230,10 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
         G.chain_kind = 0;
         if (!able) G.chain_diverged = true;   // pass 1 assumed success: its later jobs belong to another walk
         if (!exporting) {
-          off_pre = arena_alloc(G.a, lane, nx_pre);
+          off_pre = arena_alloc(G.a, lane, 2 * (long long)nx_pre);
           if (off_pre < 0) return true;
-          const double* beq = G.A(A_BEQ);
-          for (int i = lane; i < nx_pre; i += 32) G.a->arena[off_pre + i] = beq[i];
+          const double *beq = G.A(A_BEQ), *xg = G.A(A_X);
+          for (int i = lane; i < nx_pre; i += 32) { G.a->arena[off_pre + i] = beq[i]; G.a->arena[off_pre + nx_pre + i] = xg[i]; }
           __syncwarp();
         }
         fl |= SR_RESEED;
@@ -249,7 +251,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
       able = construct_profiles(G);
       if (!able) {
         if (G.last_output) fl |= SR_LAST;
-        const bool okw = write_record(G, it, fl | SR_FAIL, nx_pre, nx_mid, off_pre);
+        const bool okw = write_record(G, it, fl | SR_FAIL, nx_pre, nx_mid, off_pre, seed_r1);
         write_profile_rows(G, it);
         H.flags = G.flags;
         return !okw;
@@ -267,7 +269,7 @@ __device__ static bool run_profiles(Gal& G, GalHead& H) {
     }
     if (G.last_output) fl |= SR_LAST;
     if (!exporting) {
-      if (!write_record(G, it, fl, nx_pre, nx_mid, off_pre)) return true;
+      if (!write_record(G, it, fl, nx_pre, nx_mid, off_pre, seed_r1)) return true;
       write_profile_rows(G, it);
     }
     if (G.last_output) break;
@@ -344,9 +346,10 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkSharedT<TEAM>* rs)
       for (int v = 0; v < 3; v++) { double* f = G.A(A_F0 + v); for (int i = lane; i < G.nx; i += 32) f[i] = 0.0; }
       __syncwarp();
     } else if (R.flags & SR_RESEED) {
-      double* beq = G.A(A_BEQ);
-      for (int i = lane; i < R.nx_pre; i += 32) beq[i] = a->arena[R.off_pre + i];
+      double *beq = G.A(A_BEQ), *xg = G.A(A_X);
+      for (int i = lane; i < R.nx_pre; i += 32) { beq[i] = a->arena[R.off_pre + i]; xg[i] = a->arena[R.off_pre + R.nx_pre + i]; }
       __syncwarp();
+      G.seed_r1 = R.seed_r1;
       init_seed_field(G);
       impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
     }
@@ -365,6 +368,7 @@ __device__ static void run_evolve(Gal& G, const GalHead& H, RkSharedT<TEAM>* rs)
       break;
     }
     if (R.flags & SR_SEED0) {
+      G.seed_r1 = R.seed_r1;
       init_seed_field(G);
       impose_bc(G, G.A(A_F0), G.A(A_F1), G.A(A_F2));
     }
