@@ -153,8 +153,8 @@ typedef struct mag_params {
    * alp_m; floor-field source; critical dynamo number) and the 'Uz' output row */
   int32_t outflow_type;           /* MAG_OUTFLOW_*: 0 = 'no_outflow' */
   int32_t p_neumann_boundary_condition_rmax; /* 0; 1: dBr/dr = dBp/dr = 0 at r = R (impose_bc, gutsdynamo.f90:63-74), generic path */
-  int32_t p_use_fixed_physical_grid;         /* 0; 1 (r_max = p_rmax_over_rdisk x the largest r_disk of the history, adjust_grid does
-                                                nothing, grid.f90:69-73, :159-162) is implemented by the oracle only: mag_create rejects it */
+  int32_t p_use_fixed_physical_grid;         /* 0; 1: r_max = p_rmax_over_rdisk x the largest r_disk of the history, adjust_grid does
+                                                nothing (grid.f90:69-73, :159-162) */
   int32_t p_nn_seed;                         /* 2 ('decaying' seed) */
   int32_t reserved[3];
   double p_outflow_Lsn;           /* 1d38 */

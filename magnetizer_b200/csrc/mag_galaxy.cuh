@@ -375,7 +375,7 @@ struct ChainIn {
   const double *Sigma_d, *Sigma_star, *Rm, *Om_h, *G_h, *Om_b, *G_b;
   double *h_d, *rho_d;         // out
 };
-#define CHAIN_OK 1        // the solve did not give up
+#define CHAIN_OK 1        // the solve did not give up and no scale height is negative
 #define CHAIN_STATUS_P 2  // status 'P' was raised (log-extrapolated scale height)
 #define CHAIN_SECANT 4    // the secant fallback was used
 // Returns CHAIN_* bits.
@@ -461,6 +461,10 @@ __device__ inline int hydro_chain(const mag_params_t& P, const ChainIn& c) {
   for (int i = 1; i <= ng; i++) h_d[i - 1] = h_d[2 * ng + 2 - i - 1];
   h_d[ng] = h_d[ng + 1] + (r[ng] - r[ng + 1]) * (h_d[ng + 1] - h_d[ng + 2]) / (r[ng + 1] - r[ng + 2]);
   for (int i = 1; i <= ng + 1; i++) rho_d[i - 1] = density_to_scaleheight(h_d[i - 1], Sigma_d[i - 1]);
+  // construct_profiles tests any(h_kpc < 0) (profiles.f90:155-160): the linear extrapolation to the centre above can be
+  // negative although every root was found (a scale height that rises steeply from a tiny central value).  The arrays
+  // stay as they are -- the reference writes them out -- and the caller raises status 'H' as for a solve that gave up.
+  if (h_d[ng] < 0) return bits;
   return bits | CHAIN_OK;
 }
 

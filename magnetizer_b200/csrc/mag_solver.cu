@@ -325,9 +325,7 @@ static bool params_supported(const mag_params_t& p) {
          p.lFloor == 1 && p.p_space_varying_floor == 1 && p.p_time_varying_floor == 1 &&
          p.p_limit_turbulent_scale == 1 && p.p_allow_positive_shears == 0 && p.seed_choice >= MAG_SEED_RANDOM && p.seed_choice <= MAG_SEED_DECAYING &&
          (p.p_neumann_boundary_condition_rmax == 0 || p.p_neumann_boundary_condition_rmax == 1) &&
-         // p_use_fixed_physical_grid: the code is in place (construct_grid, adjust_grid_geometry) but the profile phase faults on some
-         // synthetic histories with it (round 2, not located yet): rejected until it is
-         p.p_use_fixed_physical_grid == 0 &&
+         (p.p_use_fixed_physical_grid == 0 || p.p_use_fixed_physical_grid == 1) &&
          p.outflow_type >= MAG_OUTFLOW_NONE && p.outflow_type <= MAG_OUTFLOW_SUPERBUBBLE && p.p_nx_ref >= 8 &&
          (p.rng_kind == 0 || p.rng_kind == 1) && p.p_nx_MAX >= p.p_nx_ref + 6;
 }

@@ -149,7 +149,7 @@ static const OtherKey kOtherKeys[] = {
     {"turb_dif", ".true.", 0},
     // grid_parameters
     {"p_rescale_field_for_shrinking_disks", ".true.", 0}, {"p_rescale_field_for_expanding_disks", ".false.", 0},
-    {"p_scale_back_f_array", ".true.", 0}, {"p_use_fixed_physical_grid", ".false.", 0}, {"p_interp_method", "simple", 0},
+    {"p_scale_back_f_array", ".true.", 0}, {"p_interp_method", "simple", 0},
     // ISM_and_disk_parameters
     {"p_check_hydro_solution", ".false.", 1}, {"p_use_fixed_turbulent_to_scaleheight_ratio", ".false.", 0},
     {"p_turbulent_to_scaleheight_ratio", "0.25", 1}, {"p_truncates_within_rreg", ".false.", 0},
@@ -190,7 +190,7 @@ inline RunConfig load_run_config(const std::string& path) {
   MAG_NL(p_variable_timesteps); MAG_NL(p_simplified_pressure); MAG_NL(p_halo_contraction); MAG_NL(p_enable_P2);
   MAG_NL(Dyn_quench); MAG_NL(Alg_quench); MAG_NL(Damp); MAG_NL(lFloor); MAG_NL(p_space_varying_floor);
   MAG_NL(p_time_varying_floor); MAG_NL(p_limit_turbulent_scale); MAG_NL(p_allow_positive_shears);
-  MAG_NL(p_neumann_boundary_condition_rmax); MAG_NL(p_nn_seed); MAG_NL(p_r_seed_decay);
+  MAG_NL(p_neumann_boundary_condition_rmax); MAG_NL(p_use_fixed_physical_grid); MAG_NL(p_nn_seed); MAG_NL(p_r_seed_decay);
   MAG_NL(p_outflow_Lsn); MAG_NL(p_outflow_fOB); MAG_NL(p_outflow_etaSN); MAG_NL(p_tOB); MAG_NL(p_N_SN1OB);
   MAG_NL(p_outflow_hot_gas_density); MAG_NL(p_outflow_nu0); MAG_NL(p_outflow_alphahot); MAG_NL(p_outflow_Vhot);
 #undef MAG_NL

@@ -415,6 +415,7 @@ _SWITCH_REF = {}
 _SWITCH_CASES = [
     # (id, settings, runs on the register loops?)
     ("neumann_outer_bc", dict(p_neumann_boundary_condition_rmax=1), False),       # gutsdynamo.f90:63-74
+    ("fixed_physical_grid", dict(p_use_fixed_physical_grid=1), True),              # grid.f90:69-73, :159-162
     ("seed_fraction", dict(seed_choice=1), True),                                  # seed_field.f90:38-41
     ("seed_decaying", dict(seed_choice=2, p_r_seed_decay=8.0, p_nn_seed=3), True),  # seed_field.f90:42-46
     ("alg_quench_without_dyn_quench", dict(Alg_quench=1, Dyn_quench=0), False),    # nvar = 2, gutsdynamo.f90:28-43, :199-209
@@ -424,7 +425,7 @@ _SWITCH_CASES = [
 
 @pytest.mark.parametrize("name,settings,fast", _SWITCH_CASES, ids=[c[0] for c in _SWITCH_CASES])
 def test_more_physics_switches(oracle, example_input, name, settings, fast):
-    """the Neumann outer boundary, the deterministic seed prescriptions and
+    """the Neumann outer boundary, the fixed physical grid, the deterministic seed prescriptions and
     the runs without the alp_m equation (nvar = 2: no 'alp_m' rows) -- 32 example + 8 synthetic galaxies each,
     on one-warp and on four-warp teams (validated on 48 + 16, profiles/r2_parity.md; every galaxy is solved
     independently of the others in both forced modes)."""
@@ -445,6 +446,12 @@ def test_more_physics_switches(oracle, example_input, name, settings, fast):
     assert not np.array_equal(ora["profiles"][0], _SWITCH_REF["ref"]["profiles"][0])   # the switch changes Br
     am = ora["profiles"][prof.index("alp_m")]
     assert (am > -9e4).any() == bool(p.Dyn_quench)                                 # ts_arrays.f90:132-138
+    if name == "fixed_physical_grid":                                              # one radial grid for the whole history
+        rk = ora["profiles"][prof.index("rkpc")]
+        for g in range(0, len(ids), 7):
+            rows = rk[g][rk[g][:, -1] > -9e4]
+            assert len(rows) == 0 or np.ptp(rows[:, -1]) == 0.0
+        assert "H" in ora["status"].tobytes().decode()     # incl. a negative scale height extrapolated to the centre (profiles.f90:155)
     s = DynamoSolver(params=p, device=0)
     try:
         for mode in (0, 2):

@@ -70,7 +70,7 @@ def test_unimplemented_switch_is_rejected_not_ignored(exe, tmp_path):
     """A namelist that sets a physics switch the CUDA path does not implement must fail loudly: running
     default physics under a non-default label would stamp wrong parameters into the output file."""
     base = open(os.path.join(ROOT, PARAMS)).read()
-    for key, val in (("Krause", ".false."), ("p_scale_back_f_array", ".false."), ("p_use_fixed_physical_grid", ".true."), ("Alp_squared", "T"), ("p_sech2_profile", ".true.")):
+    for key, val in (("Krause", ".false."), ("p_scale_back_f_array", ".false."), ("Alp_squared", "T"), ("p_sech2_profile", ".true.")):
         p = tmp_path / "bad.in"
         p.write_text(base + f"\n&dynamo_parameters\n  {key} = {val}\n/\n")
         r = subprocess.run([exe, str(p), "--dry-run"], cwd=ROOT, capture_output=True, text=True)
@@ -82,7 +82,7 @@ def test_unimplemented_switch_is_rejected_not_ignored(exe, tmp_path):
     ok = tmp_path / "ok.in"    # the default value spelled out, implemented switches, an observables key and an unknown key: accepted
     ok.write_text(base + "\n&dynamo_parameters\n  Krause = .true.\n  p_no_such_key = 3\n  p_neumann_boundary_condition_rmax = .true.\n"
                          "  p_seed_choice = 'decaying'\n  p_r_seed_decay = 12d0\n  p_nn_seed = 3\n  Dyn_quench = F\n  Alg_quench = T\n/\n"
-                         "&observables_parameters\n  p_obs_CR_alpha = 2d0\n/\n")
+                         "&grid_parameters\n  p_use_fixed_physical_grid = .true.\n/\n&observables_parameters\n  p_obs_CR_alpha = 2d0\n/\n")
     r = subprocess.run([exe, str(ok), "--dry-run"], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0 and "unknown key p_no_such_key" in r.stderr and "p_obs_cr_alpha has no effect" in r.stderr
 
