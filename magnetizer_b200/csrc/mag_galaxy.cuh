@@ -1089,6 +1089,9 @@ __device__ inline void write_field_rows(Gal& G, int it) {
       s_r += r;
     }
     warp_argmax_first(bmax, bidx);
+    // an all-NaN field never passes `bt > bmax`: maxloc then stays at the first point (as the oracle's loop does) -- the
+    // index below must not be the 'nothing found' sentinel
+    if (bidx == 0x7fffffff) { bidx = 0; bmax = CUDART_NAN; }
     s_rh = warp_sum(s_rh); s_b2rh = warp_sum(s_b2rh); s_br = warp_sum(s_br); s_r = warp_sum(s_r);
     const double rmax = rescale_at(rk, ni, bidx, nr);
     if (lane == 0) {
