@@ -53,3 +53,25 @@ def test_invalid_galaxy_reports_error(oracle, example_input):
     r = oracle.solve_batch(p, np.array([1, 2], np.int32), t, bad, nthreads=1)
     assert r["error"].tolist() == [1, 1]
     assert (r["profiles"] == -99999.0).all() and (r["status"] == b"-").all()
+
+
+def test_negative_central_scaleheight_raises_status_H(oracle, example_input):
+    """profiles.f90:155-160: `any(h_kpc<0)` ends the run with status 'H' even when every root of the hydrostatic
+    solve was found -- the linear extrapolation of h to the centre is negative when h rises steeply from a tiny
+    central value.  Reached with the fixed physical grid (grid.f90:69-73) by a synthetic history whose early disc is
+    small on the grid of its largest one; the CUDA chain missed this case until round 2."""
+    from magnetizer_b200.synthetic import galaxy_ids, synthetic_histories
+    t, inputs = example_input
+    syn = np.ascontiguousarray(synthetic_histories(inputs, 9, first=9000)[:, 8:9, :])
+    ids = galaxy_ids(9, first=9000)[8:9]
+    p = oracle.default_params()
+    p.p_use_fixed_physical_grid = 1
+    r = oracle.solve_batch(p, ids, t, syn, profiles=("h", "n", "rkpc"), scalars=("Bmax",))
+    status = r["status"].tobytes().decode()
+    assert status.rstrip("-").endswith("MH") and "H" not in status.rstrip("-")[:-1]
+    it = status.index("H")
+    h = r["profiles"][0][0][it]
+    assert (h < 0).sum() == 1 and h[0] < 0 and h[1:].min() > 0        # the rows keep the solved values, only the centre is negative
+    assert (r["profiles"][1][0][it] == 0).all()                         # rho_cgs = 0 (profiles.f90:158)
+    rk = r["profiles"][2][0]
+    assert np.ptp(rk[:it + 1, -1]) == 0.0                                 # one grid for the whole history
